@@ -1,0 +1,796 @@
+// C ABI of dibs_b200 (see include/dibs_b200.h): plan, workspace, launch logic, CUDA-graph replay, NCCL.
+#include "../../include/dibs_b200.h"
+
+#include <dlfcn.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_mc.cuh"
+#include "kernels_mc_bge.cuh"
+#include "bge_prepare.cuh"
+#include "kernels_mc_nn.cuh"
+#include "kernels_prior.cuh"
+#include "kernels_pair.cuh"
+#include "kernels_init.cuh"
+
+using namespace dibs;
+
+// ------------------------------------------------------------------------------------------
+// errors, launch accounting
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(DIBS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e) + " (" + \
+                                           __FILE__ + ":" + std::to_string(__LINE__) + ")");       \
+    } while (0)
+
+#define LAUNCHED()                                                                                 \
+    do {                                                                                           \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                        \
+        CU(cudaGetLastError());                                                                    \
+    } while (0)
+
+#define TRY(expr)                \
+    do {                         \
+        int _r = (expr);         \
+        if (_r != DIBS_OK) return _r; \
+    } while (0)
+
+extern "C" const char* dibs_last_error(void) { return g_last_error.c_str(); }
+extern "C" int dibs_abi_version(void) { return 1; }
+extern "C" int64_t dibs_launch_count(void) { return (int64_t)g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------
+// NCCL through dlopen (the process normally has torch's libnccl.so.2 loaded already)
+// ------------------------------------------------------------------------------------------
+struct NcclId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.lib) return DIBS_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    if (const char* env = getenv("DIBS_B200_NCCL_LIB")) lib = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    for (int i = 0; i < 2 && !lib; ++i) lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(DIBS_ERR_NCCL, std::string("dlopen(libnccl.so.2) failed: ") + dlerror());
+    g_nccl.GetUniqueId = (int (*)(NcclId*))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(NcclComm*, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(NcclComm))dlsym(lib, "ncclCommDestroy");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))dlsym(lib, "ncclAllGather");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy)
+        return fail(DIBS_ERR_NCCL, "libnccl is missing a required symbol");
+    g_nccl.lib = lib;
+    return DIBS_OK;
+}
+#define NC(call)                                                                                     \
+    do {                                                                                             \
+        int _r = (call);                                                                             \
+        if (_r != 0)                                                                                 \
+            return fail(DIBS_ERR_NCCL, std::string(#call) + ": " +                                   \
+                                           (g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?")); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+struct dibs_plan {
+    dibs_config cfg;
+    int d, k, M, M_loc, row0, Dz, Dth, D, ld;
+    int N = 0;
+    bool has_data = false, has_mask = false;
+    int dmax = 0;
+    // derived fp32 constants, rounded like the reference
+    float s2, log2pis2, sig2_edge, lognorm_edge, sig2_param, lognorm_param, er_coef, sigma_z2;
+    // data
+    float* x = nullptr; int32_t* mask = nullptr;
+    double* bge_r = nullptr; float* bge_table = nullptr; float* bge_coef = nullptr; int bge_r_stride = 0;
+    // particle state: two packed buffers [M][ld], row = [Z | Theta | dZ | dTheta]
+    float* pk[2] = {nullptr, nullptr};
+    float* v = nullptr;            // [M_loc][D]
+    float* base = nullptr;         // [M_loc]
+    StepState* st = nullptr;
+    // MC workspace
+    int gpb_th = 1, gpb_z = 1, th_chunks = 1, z_chunks = 1, th_spc = 1, z_spc = 1, th_acc_size = 0;
+    float *th_acc = nullptr, *th_stats = nullptr, *z_acc = nullptr, *z_stats = nullptr, *acyc = nullptr;
+    // pairwise workspace
+    int n_split = 1, split_len = 0;
+    float *dist_part = nullptr, *kz = nullptr, *kt = nullptr, *kfull = nullptr;
+    // CUDA graphs of one step, per buffer parity
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    int kernels_per_step = 0;
+    bool use_graph = true;
+    // NCCL
+    NcclComm comm = nullptr;
+};
+
+static int pick_dmax(int d) {
+    const int opts[] = {8, 16, 20, 32, 64, 128};
+    for (int o : opts) if (d <= o) return o;
+    return 0;
+}
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+extern "C" int dibs_theta_dim(const dibs_plan* plan) { return plan ? plan->Dth : 0; }
+
+static void choose_chunks(int S, int gpb, int n_local, int* chunks, int* spc) {
+    int max_chunks = ceil_div(S, gpb);
+    int want = ceil_div(2 * 148, n_local > 0 ? n_local : 1);
+    if (want < 1) want = 1;
+    if (want > max_chunks) want = max_chunks;
+    int per = ceil_div(ceil_div(S, want), gpb) * gpb;
+    *spc = per;
+    *chunks = ceil_div(S, per);
+}
+
+extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
+    if (!cfg || !out) return fail(DIBS_ERR_INVALID_ARG, "null argument");
+    const dibs_config& c = *cfg;
+    if (c.n_vars < 2 || c.n_dim < 1 || c.n_particles < 1) return fail(DIBS_ERR_INVALID_ARG, "n_vars>=2, n_dim>=1, n_particles>=1 required");
+    if (c.n_grad_mc_samples < 1 || c.n_acyclicity_mc_samples < 1) return fail(DIBS_ERR_INVALID_ARG, "MC sample counts must be positive");
+    if (c.grad_estimator_z != DIBS_ESTIMATOR_SCORE && c.grad_estimator_z != DIBS_ESTIMATOR_REPARAM)
+        return fail(DIBS_ERR_INVALID_ARG, "Unknown gradient estimator");
+    if (c.optimizer != DIBS_OPT_GD && c.optimizer != DIBS_OPT_RMSPROP) return fail(DIBS_ERR_INVALID_ARG, "unknown optimizer");
+    if (c.graph_prior < 0 || c.graph_prior > 2) return fail(DIBS_ERR_INVALID_ARG, "unknown graph prior");
+    if (c.world_size < 1 || c.rank < 0 || c.rank >= c.world_size || c.n_particles % c.world_size)
+        return fail(DIBS_ERR_INVALID_ARG, "n_particles must be divisible by world_size and 0 <= rank < world_size");
+    if (c.joint && c.likelihood == DIBS_LIK_BGE) return fail(DIBS_ERR_INVALID_ARG, "BGe is a marginal likelihood: use MarginalDiBS");
+    if (!c.joint && c.likelihood != DIBS_LIK_BGE) return fail(DIBS_ERR_UNSUPPORTED, "MarginalDiBS is implemented for BGe only");
+    if (c.likelihood == DIBS_LIK_BGE && c.grad_estimator_z != DIBS_ESTIMATOR_SCORE)
+        return fail(DIBS_ERR_UNSUPPORTED, "BGe + reparam estimator is not implemented natively (SURVEY 8f rank 3)");
+    if (c.likelihood < 0 || c.likelihood > 2) return fail(DIBS_ERR_UNSUPPORTED, "unknown likelihood model");
+    if (c.likelihood == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN && (c.hidden < 1 || c.hidden > 32))
+        return fail(DIBS_ERR_UNSUPPORTED, "DenseNonlinearGaussian: one hidden layer of 1..32 units is implemented");
+    if (pick_dmax(c.n_vars) == 0) return fail(DIBS_ERR_UNSUPPORTED, "n_vars > 128 is not implemented");
+    if (c.likelihood == DIBS_LIK_BGE && c.n_vars > 64) return fail(DIBS_ERR_UNSUPPORTED, "BGe: n_vars > 64 is not implemented");
+
+    dibs_plan* p = new dibs_plan();
+    p->cfg = c;
+    p->d = c.n_vars; p->k = c.n_dim; p->M = c.n_particles;
+    p->M_loc = c.n_particles / c.world_size; p->row0 = c.rank * p->M_loc;
+    p->Dz = 2 * p->d * p->k;
+    p->Dth = 0;
+    if (c.likelihood == DIBS_LIK_LINEAR_GAUSSIAN) p->Dth = p->d * p->d;
+    if (c.likelihood == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN) p->Dth = p->d * (p->d * c.hidden + 2 * c.hidden + 1);
+    p->D = p->Dz + p->Dth;
+    p->ld = 2 * p->D;
+    p->dmax = pick_dmax(p->d);
+    // fp32 constants with the reference's rounding: scale = sqrt(obs_noise); scale^2; log(2 pi scale^2)
+    float scale = sqrtf(c.obs_noise);
+    p->s2 = scale * scale;
+    p->log2pis2 = logf(6.283185307179586f * p->s2);
+    p->sig2_edge = c.sig_edge * c.sig_edge;
+    p->lognorm_edge = logf(6.283185307179586f * p->sig2_edge);
+    p->sig2_param = c.sig_param * c.sig_param;
+    p->lognorm_param = logf(6.283185307179586f * p->sig2_param);
+    p->er_coef = logf(c.er_p) - logf(1.0f - c.er_p);       // NaN / inf for p >= 1 like graph.py:108
+    p->sigma_z2 = powf(c.latent_prior_std, 2.0f);           // latent_prior_std ** 2.0 (dibs.py:657)
+    if (const char* e = getenv("DIBS_B200_NO_GRAPH")) p->use_graph = !(e[0] == '1');
+
+    const int d = p->d, S = c.n_grad_mc_samples;
+    int per_item = (c.likelihood == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN) ? d * nn_hp(c.hidden) : d;
+    int gpb = 256 / per_item; if (gpb < 1) gpb = 1; if (gpb > S) gpb = S;
+    p->gpb_th = p->gpb_z = gpb;
+    choose_chunks(S, gpb, p->M_loc, &p->th_chunks, &p->th_spc);
+    p->z_chunks = p->th_chunks; p->z_spc = p->th_spc;
+    p->th_acc_size = p->Dth;
+
+    auto alloc = [&](void** ptr, size_t bytes) -> int {
+        CU(cudaMalloc(ptr, bytes ? bytes : 4));
+        CU(cudaMemset(*ptr, 0, bytes ? bytes : 4));
+        return DIBS_OK;
+    };
+    int r = DIBS_OK;
+    size_t pk_bytes = (size_t)p->M * p->ld * sizeof(float);
+    if ((r = alloc((void**)&p->pk[0], pk_bytes)) || (r = alloc((void**)&p->pk[1], pk_bytes)) ||
+        (r = alloc((void**)&p->v, (size_t)p->M_loc * p->D * sizeof(float))) ||
+        (r = alloc((void**)&p->base, (size_t)p->M_loc * sizeof(float))) ||
+        (r = alloc((void**)&p->st, sizeof(StepState))) ||
+        (r = alloc((void**)&p->z_acc, (size_t)p->M_loc * p->z_chunks * d * d * sizeof(float))) ||
+        (r = alloc((void**)&p->z_stats, (size_t)p->M_loc * p->z_chunks * 4 * sizeof(float))) ||
+        (r = alloc((void**)&p->th_acc, (size_t)p->M_loc * p->th_chunks * p->th_acc_size * sizeof(float))) ||
+        (r = alloc((void**)&p->th_stats, (size_t)p->M_loc * p->th_chunks * 4 * sizeof(float))) ||
+        (r = alloc((void**)&p->acyc, (size_t)p->M_loc * d * d * sizeof(float)))) {
+        dibs_plan_destroy(p);
+        return r;
+    }
+    // pairwise: split the feature axis until the distance pass has >= ~148 CTAs
+    int tiles = ceil_div(p->M, KT) * ceil_div(p->M_loc, KT);
+    int ns = ceil_div(148, tiles);
+    int max_ns = ceil_div(p->D, 2 * KF);
+    if (ns > max_ns) ns = max_ns;
+    if (ns < 1) ns = 1;
+    p->split_len = ceil_div(ceil_div(p->D, ns), KF) * KF;
+    p->n_split = ceil_div(p->D, p->split_len);
+    size_t plane = (size_t)p->M_loc * p->M * sizeof(float);
+    if ((r = alloc((void**)&p->dist_part, plane * 2 * p->n_split)) || (r = alloc((void**)&p->kz, plane)) ||
+        (r = alloc((void**)&p->kt, plane)) || (r = alloc((void**)&p->kfull, plane))) {
+        dibs_plan_destroy(p);
+        return r;
+    }
+    *out = p;
+    return DIBS_OK;
+}
+
+extern "C" int dibs_plan_destroy(dibs_plan* p) {
+    if (!p) return DIBS_OK;
+    for (int i = 0; i < 2; ++i) if (p->gexec[i]) cudaGraphExecDestroy(p->gexec[i]);
+    if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
+    void* ptrs[] = {p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->v, p->base, p->st,
+                    p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->dist_part, p->kz, p->kt, p->kfull};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    delete p;
+    return DIBS_OK;
+}
+
+extern "C" int dibs_set_data(dibs_plan* p, const float* x, const int32_t* mask, int32_t n_obs,
+                             const float* bge_mean_obs_host, void* stream_) {
+    if (!p || !x || n_obs < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_set_data: bad arguments");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int d = p->d;
+    for (int i = 0; i < 2; ++i) if (p->gexec[i]) { cudaGraphExecDestroy(p->gexec[i]); p->gexec[i] = nullptr; }
+    if (p->x) { cudaFree(p->x); p->x = nullptr; }
+    if (p->mask) { cudaFree(p->mask); p->mask = nullptr; }
+    p->N = n_obs;
+    CU(cudaMalloc((void**)&p->x, (size_t)n_obs * d * sizeof(float)));
+    CU(cudaMemcpyAsync(p->x, x, (size_t)n_obs * d * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    p->has_mask = false;
+    if (mask) {
+        // an all-zero mask is the observational case (svgd.py:86-87): detect it once so kernels skip masking
+        std::vector<int32_t> h((size_t)n_obs * d);
+        CU(cudaMemcpyAsync(h.data(), mask, h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        for (int32_t v : h) if (v) { p->has_mask = true; break; }
+        if (p->has_mask) {
+            CU(cudaMalloc((void**)&p->mask, h.size() * sizeof(int32_t)));
+            CU(cudaMemcpyAsync(p->mask, mask, h.size() * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+        }
+    }
+    if (p->cfg.likelihood == DIBS_LIK_BGE) TRY(bge_prepare(p->cfg, d, n_obs, p->x, p->mask, bge_mean_obs_host, &p->bge_r,
+                                                       &p->bge_table, &p->bge_coef, &p->bge_r_stride, stream, g_last_error));
+    p->has_data = true;
+    return DIBS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------
+struct Src {                 // where the particles of a launch live
+    const float* z; int z_ld;
+    const float* theta; int th_ld;
+    int n; int m_offset;
+    const StepState* st;
+    const uint32_t* keys; int t;
+};
+
+static void fill_mc(const dibs_plan* p, const Src& s, McParams& q) {
+    memset(&q, 0, sizeof(q));
+    q.z = s.z; q.z_ld = s.z_ld; q.theta = s.theta; q.th_ld = s.th_ld;
+    q.n_local = s.n; q.m_offset = s.m_offset; q.n_particles = p->M;
+    q.d = p->d; q.k = p->k; q.n_obs = p->N; q.n_samples = p->cfg.n_grad_mc_samples;
+    q.x = p->x; q.mask = p->has_mask ? p->mask : nullptr;
+    q.st = s.st; q.partitionable = p->cfg.prng_partitionable;
+    q.keys_override = s.keys; q.t_override = s.t;
+    q.alpha_linear = p->cfg.alpha_linear; q.tau = p->cfg.tau;
+    q.s2 = p->s2; q.log2pis2 = p->log2pis2;
+    q.mean_edge = p->cfg.mean_edge; q.sig2_edge = p->sig2_edge; q.lognorm_edge = p->lognorm_edge;
+    if (p->cfg.likelihood == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN) {
+        q.mean_edge = 0.0f; q.sig2_edge = p->sig2_param; q.lognorm_edge = p->lognorm_param;
+    }
+    q.hidden = p->cfg.hidden; q.hp = nn_hp(p->cfg.hidden);
+    q.bge_r = p->bge_r; q.bge_r_stride = p->bge_r_stride; q.bge_table = p->bge_table; q.bge_coef = p->bge_coef;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    if (bytes > 227 * 1024) return fail(DIBS_ERR_UNSUPPORTED, "problem size needs more than 227 KB of shared memory per CTA");
+    if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return DIBS_OK;
+}
+
+#define DECL_MC(FAM, DM) namespace dibs { int launch_mc_##FAM##_##DM(int, const McParams&, dim3, size_t, cudaStream_t); }
+DECL_MC(lingauss, 8) DECL_MC(lingauss, 16) DECL_MC(lingauss, 20) DECL_MC(lingauss, 32) DECL_MC(lingauss, 64) DECL_MC(lingauss, 128)
+DECL_MC(nn, 8) DECL_MC(nn, 16) DECL_MC(nn, 20) DECL_MC(nn, 32) DECL_MC(nn, 64) DECL_MC(nn, 128)
+DECL_MC(bge, 8) DECL_MC(bge, 16) DECL_MC(bge, 20) DECL_MC(bge, 32) DECL_MC(bge, 64)
+#undef DECL_MC
+
+// the register-tiled MC kernels are instantiated per DMAX in mc_*_inst.cu (parallel build)
+template <int MODE>
+static int launch_mc(const dibs_plan* p, McParams q, cudaStream_t stream) {
+    dim3 grid(q.n_local, q.n_chunks);
+    const int lik = p->cfg.likelihood;
+    size_t smem = 0;
+    int e = 0;
+    if (lik == DIBS_LIK_LINEAR_GAUSSIAN) {
+        smem = mc_lingauss_smem(p->d, p->k, p->N, q.gpb, p->dmax, q.mask != nullptr);
+    } else if (lik == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN) {
+        smem = mc_nn_smem(p->d, p->k, p->N, q.gpb, p->dmax, q.hidden, q.hp, q.mask != nullptr);
+    } else {
+        if (MODE != MC_Z_SCORE && MODE != MC_LP_ONLY) return fail(DIBS_ERR_UNSUPPORTED, "BGe supports the score estimator only");
+        smem = mc_bge_smem(p->d, p->k, q.gpb);
+    }
+    if (smem > 227 * 1024) return fail(DIBS_ERR_UNSUPPORTED, "problem size needs more than 227 KB of shared memory per CTA");
+#define GO(FAM) switch (p->dmax) { case 8: e = launch_mc_##FAM##_8(MODE, q, grid, smem, stream); break; \
+        case 16: e = launch_mc_##FAM##_16(MODE, q, grid, smem, stream); break; \
+        case 20: e = launch_mc_##FAM##_20(MODE, q, grid, smem, stream); break; \
+        case 32: e = launch_mc_##FAM##_32(MODE, q, grid, smem, stream); break; \
+        case 64: e = launch_mc_##FAM##_64(MODE, q, grid, smem, stream); break; \
+        default: e = launch_mc_##FAM##_LAST(MODE, q, grid, smem, stream); break; }
+#define launch_mc_lingauss_LAST launch_mc_lingauss_128
+#define launch_mc_nn_LAST launch_mc_nn_128
+#define launch_mc_bge_LAST launch_mc_bge_64
+    if (lik == DIBS_LIK_LINEAR_GAUSSIAN) GO(lingauss)
+    else if (lik == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN) GO(nn)
+    else GO(bge)
+#undef GO
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != 0) return fail(DIBS_ERR_CUDA, std::string("MC kernel launch: ") + cudaGetErrorString((cudaError_t)e));
+    return DIBS_OK;
+}
+
+static int launch_acyc(const dibs_plan* p, const Src& s, int which_split, float* ds_out, cudaStream_t stream) {
+    AcycParams a;
+    memset(&a, 0, sizeof(a));
+    a.z = s.z; a.z_ld = s.z_ld; a.n_local = s.n; a.m_offset = s.m_offset; a.n_particles = p->M;
+    a.d = p->d; a.k = p->k; a.n_samples = p->cfg.n_acyclicity_mc_samples;
+    a.st = s.st; a.which_split = which_split; a.partitionable = p->cfg.prng_partitionable;
+    a.keys_override = s.keys; a.t_override = s.t;
+    a.alpha_linear = p->cfg.alpha_linear; a.tau = p->cfg.tau; a.ds_out = ds_out;
+    const int d = p->d;
+    if (d <= 32) {
+        int warps = a.n_samples < 8 ? a.n_samples : 8;
+        size_t smem = acyclic_smem(d, p->k, warps);
+        while (smem > 200 * 1024 && warps > 1) { warps /= 2; smem = acyclic_smem(d, p->k, warps); }
+        TRY(set_smem(k_acyclic_grad<true>, smem));
+        k_acyclic_grad<true><<<s.n, warps * 32, smem, stream>>>(a);
+    } else {
+        size_t smem = acyclic_smem(d, p->k, 1);
+        TRY(set_smem(k_acyclic_grad<false>, smem));
+        k_acyclic_grad<false><<<s.n, 256, smem, stream>>>(a);
+    }
+    LAUNCHED();
+    return DIBS_OK;
+}
+
+static void fill_asm(const dibs_plan* p, const Src& s, AsmParams& a) {
+    memset(&a, 0, sizeof(a));
+    a.z = s.z; a.z_ld = s.z_ld; a.n_local = s.n; a.d = p->d; a.k = p->k;
+    a.st = s.st; a.t_override = s.t;
+    a.alpha_linear = p->cfg.alpha_linear; a.beta_linear = p->cfg.beta_linear;
+    a.n_samples = p->cfg.n_grad_mc_samples; a.sf_coef = p->cfg.score_function_baseline;
+    a.n_acyc = p->cfg.n_acyclicity_mc_samples;
+    a.prior_kind = p->cfg.graph_prior; a.er_coef = p->er_coef; a.sigma_z2 = p->sigma_z2;
+    a.z_mode = p->cfg.grad_estimator_z == DIBS_ESTIMATOR_SCORE ? MC_Z_SCORE : MC_Z_REPARAM;
+}
+
+static int launch_asm(const dibs_plan* p, const AsmParams& a, cudaStream_t stream) {
+    size_t smem = assemble_smem(p->d, p->k);
+    TRY(set_smem(k_assemble_grad, smem));
+    k_assemble_grad<<<a.n_local, 256, smem, stream>>>(a);
+    LAUNCHED();
+    return DIBS_OK;
+}
+
+// gradient phase for `s.n` particles: MC passes -> acyclicity -> assemble
+static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_stats, float* z_acc, float* z_stats,
+                         float* acyc, const float* base_in, float* base_out, float* grad_z, int gz_ld, float* grad_th,
+                         int gth_ld, cudaStream_t stream) {
+    const bool joint = p->cfg.joint;
+    McParams q;
+    if (joint) {
+        fill_mc(p, s, q);
+        q.which_split = 0; q.pre_split = 0;
+        q.n_chunks = p->th_chunks; q.s_per_chunk = p->th_spc; q.gpb = p->gpb_th;
+        q.part_acc = th_acc; q.acc_size = p->th_acc_size; q.part_stats = th_stats;
+        TRY(launch_mc<MC_THETA_HARD>(p, q, stream));
+    }
+    fill_mc(p, s, q);
+    q.which_split = joint ? 1 : 0; q.pre_split = 1;
+    q.n_chunks = p->z_chunks; q.s_per_chunk = p->z_spc; q.gpb = p->gpb_z;
+    q.part_acc = z_acc; q.acc_size = p->d * p->d; q.part_stats = z_stats;
+    if (p->cfg.grad_estimator_z == DIBS_ESTIMATOR_SCORE) TRY(launch_mc<MC_Z_SCORE>(p, q, stream));
+    else TRY(launch_mc<MC_Z_REPARAM>(p, q, stream));
+    TRY(launch_acyc(p, s, joint ? 2 : 1, acyc, stream));
+    AsmParams a;
+    fill_asm(p, s, a);
+    a.zacc = z_acc; a.zstats = z_stats; a.z_chunks = p->z_chunks;
+    a.baselines_in = base_in; a.baselines_out = base_out;
+    if (joint) { a.thacc = th_acc; a.thstats = th_stats; a.th_chunks = p->th_chunks; a.th_dim = p->Dth; }
+    a.acyc = acyc;
+    a.grad_z = grad_z; a.gz_ld = gz_ld; a.grad_th = grad_th; a.gth_ld = gth_ld;
+    TRY(launch_asm(p, a, stream));
+    return DIBS_OK;
+}
+
+static void fill_pair(const dibs_plan* p, PairParams& q) {
+    memset(&q, 0, sizeof(q));
+    q.n_all = p->M; q.row0 = p->row0; q.n_rows = p->M_loc; q.dz = p->Dz; q.dth = p->Dth;
+    q.n_split = p->n_split; q.split_len = p->split_len; q.dist_part = p->dist_part;
+    q.kz = p->kz; q.kt = p->Dth ? p->kt : nullptr; q.kfull = p->kfull;
+    q.h_z = p->cfg.h_latent; q.h_t = p->cfg.h_theta; q.scale_z = p->cfg.scale_latent; q.scale_t = p->cfg.scale_theta;
+    q.optimizer = p->cfg.optimizer; q.stepsize = p->cfg.stepsize;
+    q.n_particles = p->M; q.partitionable = p->cfg.prng_partitionable;
+    q.n_step_splits = p->cfg.joint ? 3 : 2;
+}
+
+static int launch_pair(const PairParams& q, bool with_phi, cudaStream_t stream) {
+    dim3 g1(ceil_div(q.n_all, KT), ceil_div(q.n_rows, KT), q.n_split);
+    k_pair_dist<<<g1, 256, 0, stream>>>(q);
+    LAUNCHED();
+    size_t plane = (size_t)q.n_rows * q.n_all;
+    int blocks = (int)((plane + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+    k_pair_finish<<<blocks, 256, 0, stream>>>(q);
+    LAUNCHED();
+    if (with_phi) {
+        dim3 g3(ceil_div(q.dz, PT_C) + ceil_div(q.dth, PT_C), ceil_div(q.n_rows, PT_I));
+        k_phi_update<<<g3, 64, 0, stream>>>(q);
+        LAUNCHED();
+    }
+    return DIBS_OK;
+}
+
+// one full _svgd_step on the packed buffers; reads pk[cur], writes the updated local rows into pk[cur^1]
+static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream) {
+    float* P = p->pk[cur];
+    float* Pn = p->pk[cur ^ 1];
+    float* loc = P + (size_t)p->row0 * p->ld;
+    Src s{loc, p->ld, p->Dth ? loc + p->Dz : nullptr, p->ld, p->M_loc, p->row0, p->st, nullptr, 0};
+    TRY(enqueue_grads(p, s, p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->base, p->base,
+                      loc + p->D, p->ld, p->Dth ? loc + p->D + p->Dz : nullptr, p->ld, stream));
+    if (p->cfg.world_size > 1) {
+        if (!p->comm) return fail(DIBS_ERR_STATE, "world_size > 1 but no NCCL communicator attached");
+        // the one exchange of the step: every rank contributes its rows [Z | Theta | dZ | dTheta] (in place)
+        NC(g_nccl.AllGather(loc, P, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm, stream));
+    }
+    PairParams q;
+    fill_pair(p, q);
+    q.x_all = P; q.ld = p->ld; q.g_all = P + p->D; q.g_ld = p->ld;
+    q.x_next = Pn + (size_t)p->row0 * p->ld; q.next_ld = p->ld;
+    q.v = p->v; q.v_ld = p->D;
+    q.st = p->st;
+    TRY(launch_pair(q, true, stream));
+    return DIBS_OK;
+}
+
+__global__ void k_set_state(StepState* st, const uint32_t* key, int t) {
+    st->key[0] = key[0]; st->key[1] = key[1]; st->t = t; st->pad = 0;
+}
+__global__ void k_get_key(const StepState* st, uint32_t* key) { key[0] = st->key[0]; key[1] = st->key[1]; }
+
+extern "C" int dibs_svgd_steps(dibs_plan* p, int32_t t_start, int32_t n_steps, float* z, float* theta, float* v_z,
+                               float* v_theta, uint32_t* key, float* sf_baseline, void* stream_) {
+    if (!p || !z || !key || !sf_baseline) return fail(DIBS_ERR_INVALID_ARG, "dibs_svgd_steps: null argument");
+    if (!p->has_data) return fail(DIBS_ERR_STATE, "dibs_set_data has not been called");
+    if (p->Dth && !theta) return fail(DIBS_ERR_INVALID_ARG, "theta is required for joint inference");
+    const bool rms = p->cfg.optimizer == DIBS_OPT_RMSPROP;
+    if (rms && (!v_z || (p->Dth && !v_theta))) return fail(DIBS_ERR_INVALID_ARG, "rmsprop needs v_z / v_theta");
+    if (n_steps <= 0) return DIBS_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t fz = sizeof(float) * p->Dz, ft = sizeof(float) * p->Dth, fl = sizeof(float) * p->ld, fd = sizeof(float) * p->D;
+    float* loc0 = p->pk[0] + (size_t)p->row0 * p->ld;
+    // pack caller-owned arrays into the plan's row layout
+    CU(cudaMemcpy2DAsync(loc0, fl, z, fz, fz, p->M_loc, cudaMemcpyDeviceToDevice, stream));
+    if (p->Dth) CU(cudaMemcpy2DAsync(loc0 + p->Dz, fl, theta, ft, ft, p->M_loc, cudaMemcpyDeviceToDevice, stream));
+    if (rms) {
+        CU(cudaMemcpy2DAsync(p->v, fd, v_z, fz, fz, p->M_loc, cudaMemcpyDeviceToDevice, stream));
+        if (p->Dth) CU(cudaMemcpy2DAsync(p->v + p->Dz, fd, v_theta, ft, ft, p->M_loc, cudaMemcpyDeviceToDevice, stream));
+    }
+    CU(cudaMemcpyAsync(p->base, sf_baseline, sizeof(float) * p->M_loc, cudaMemcpyDeviceToDevice, stream));
+    k_set_state<<<1, 1, 0, stream>>>(p->st, key, t_start);
+    LAUNCHED();
+
+    const bool graph = p->use_graph && p->cfg.world_size == 1;
+    if (graph && !p->gexec[0]) {
+        for (int par = 0; par < 2; ++par) {
+            long long before = g_launches.load();
+            cudaGraph_t g = nullptr;
+            CU(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            int r = enqueue_step(p, par, stream);
+            cudaError_t e = cudaStreamEndCapture(stream, &g);
+            if (r != DIBS_OK) { if (g) cudaGraphDestroy(g); return r; }
+            if (e != cudaSuccess) return fail(DIBS_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+            CU(cudaGraphInstantiate(&p->gexec[par], g, 0));
+            cudaGraphDestroy(g);
+            p->kernels_per_step = (int)(g_launches.load() - before);
+            g_launches.store(before);   // captured, not executed
+        }
+    }
+    for (int i = 0; i < n_steps; ++i) {
+        int cur = i & 1;
+        if (graph) {
+            CU(cudaGraphLaunch(p->gexec[cur], stream));
+            g_launches.fetch_add(p->kernels_per_step, std::memory_order_relaxed);
+        } else {
+            TRY(enqueue_step(p, cur, stream));
+        }
+    }
+    float* locf = p->pk[n_steps & 1] + (size_t)p->row0 * p->ld;
+    CU(cudaMemcpy2DAsync(z, fz, locf, fl, fz, p->M_loc, cudaMemcpyDeviceToDevice, stream));
+    if (p->Dth) CU(cudaMemcpy2DAsync(theta, ft, locf + p->Dz, fl, ft, p->M_loc, cudaMemcpyDeviceToDevice, stream));
+    if (rms) {
+        CU(cudaMemcpy2DAsync(v_z, fz, p->v, fd, fz, p->M_loc, cudaMemcpyDeviceToDevice, stream));
+        if (p->Dth) CU(cudaMemcpy2DAsync(v_theta, ft, p->v + p->Dz, fd, ft, p->M_loc, cudaMemcpyDeviceToDevice, stream));
+    }
+    CU(cudaMemcpyAsync(sf_baseline, p->base, sizeof(float) * p->M_loc, cudaMemcpyDeviceToDevice, stream));
+    k_get_key<<<1, 1, 0, stream>>>(p->st, key);
+    LAUNCHED();
+    return DIBS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// NCCL attach
+// ------------------------------------------------------------------------------------------
+extern "C" int dibs_nccl_unique_id(uint8_t* id128) {
+    if (!id128) return fail(DIBS_ERR_INVALID_ARG, "null id buffer");
+    TRY(nccl_load());
+    NcclId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(id128, id.internal, 128);
+    return DIBS_OK;
+}
+
+extern "C" int dibs_plan_attach_nccl(dibs_plan* p, const uint8_t* id128) {
+    if (!p || !id128) return fail(DIBS_ERR_INVALID_ARG, "null argument");
+    TRY(nccl_load());
+    NcclId id;
+    memcpy(id.internal, id128, 128);
+    NC(g_nccl.CommInitRank(&p->comm, p->cfg.world_size, id, p->cfg.rank));
+    return DIBS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// init
+// ------------------------------------------------------------------------------------------
+extern "C" int dibs_init_particles(dibs_plan* p, const uint32_t* key, float* z_all, float* theta_all, void* stream_) {
+    if (!p || !key || !z_all) return fail(DIBS_ERR_INVALID_ARG, "dibs_init_particles: null argument");
+    if (p->Dth && !theta_all) return fail(DIBS_ERR_INVALID_ARG, "theta buffer required");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    InitParams q;
+    q.key = key; q.M = p->M; q.d = p->d; q.k = p->k; q.std_z = p->cfg.latent_prior_std; q.z = z_all; q.theta = theta_all;
+    q.lik = p->cfg.likelihood; q.hidden = p->cfg.hidden; q.partitionable = p->cfg.prng_partitionable;
+    q.mean_edge = p->cfg.mean_edge; q.sig_edge = p->cfg.sig_edge; q.min_edge = p->cfg.min_edge; q.sig_param = p->cfg.sig_param;
+    q.dth = p->Dth;
+    size_t nz = (size_t)p->M * p->Dz;
+    k_init_z<<<(int)((nz + 255) / 256), 256, 0, stream>>>(q);
+    LAUNCHED();
+    if (p->cfg.likelihood == DIBS_LIK_LINEAR_GAUSSIAN) {
+        size_t nt = (size_t)p->M * p->Dth;
+        k_init_theta_lin<<<(int)((nt + 255) / 256), 256, 0, stream>>>(q);
+        LAUNCHED();
+    } else if (p->cfg.likelihood == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN) {
+        k_init_theta_nn<<<ceil_div(p->M * p->d, 4), 128, 0, stream>>>(q);
+        LAUNCHED();
+    }
+    return DIBS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// hooks
+// ------------------------------------------------------------------------------------------
+struct Scratch {
+    std::vector<void*> ptrs;
+    ~Scratch() { for (void* q : ptrs) cudaFree(q); }
+    template <typename T> int get(T** out, size_t count) {
+        void* q = nullptr;
+        CU(cudaMalloc(&q, (count ? count : 1) * sizeof(T)));
+        ptrs.push_back(q);
+        *out = (T*)q;
+        return DIBS_OK;
+    }
+};
+
+extern "C" int dibs_edge_probs(dibs_plan* p, const float* z, int32_t n, int32_t t, float* p_out, void* stream_) {
+    if (!p || !z || !p_out || n < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_edge_probs: bad arguments");
+    size_t smem = (size_t)2 * p->d * p->k * sizeof(float);
+    TRY(set_smem(k_edge_probs, smem));
+    k_edge_probs<<<n, 256, smem, (cudaStream_t)stream_>>>(z, p->Dz, p->d, p->k, p->cfg.alpha_linear * (float)t, p_out, nullptr);
+    LAUNCHED();
+    return DIBS_OK;
+}
+
+extern "C" int dibs_particle_to_g_lim(dibs_plan* p, const float* z, int32_t n, int32_t* g_out, void* stream_) {
+    if (!p || !z || !g_out || n < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_particle_to_g_lim: bad arguments");
+    size_t smem = (size_t)2 * p->d * p->k * sizeof(float);
+    TRY(set_smem(k_edge_probs, smem));
+    k_edge_probs<<<n, 256, smem, (cudaStream_t)stream_>>>(z, p->Dz, p->d, p->k, 0.0f, nullptr, g_out);
+    LAUNCHED();
+    return DIBS_OK;
+}
+
+extern "C" int dibs_sample_graphs(dibs_plan* p, const float* probs, const uint32_t* keys, int32_t n, int32_t n_samples,
+                                  int32_t* g_out, void* stream_) {
+    if (!p || !probs || !keys || !g_out || n < 1 || n_samples < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_sample_graphs: bad arguments");
+    size_t smem = ((size_t)p->d * p->d + 2 * p->d * p->k) * sizeof(float);
+    TRY(set_smem(k_sample_graphs, smem));
+    k_sample_graphs<<<n, 256, smem, (cudaStream_t)stream_>>>(probs, p->d * p->d, keys, p->d, p->k, n_samples, 1, 0.0f, 0.0f,
+                                                            p->cfg.prng_partitionable, g_out, nullptr);
+    LAUNCHED();
+    return DIBS_OK;
+}
+
+extern "C" int dibs_soft_graphs(dibs_plan* p, const float* z, const uint32_t* keys, int32_t n, int32_t n_samples,
+                                int32_t t, float* g_out, void* stream_) {
+    if (!p || !z || !keys || !g_out || n < 1 || n_samples < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_soft_graphs: bad arguments");
+    size_t smem = ((size_t)p->d * p->d + 2 * p->d * p->k) * sizeof(float);
+    TRY(set_smem(k_sample_graphs, smem));
+    k_sample_graphs<<<n, 256, smem, (cudaStream_t)stream_>>>(z, p->Dz, keys, p->d, p->k, n_samples, 0,
+                                                            p->cfg.alpha_linear * (float)t, p->cfg.tau,
+                                                            p->cfg.prng_partitionable, nullptr, g_out);
+    LAUNCHED();
+    return DIBS_OK;
+}
+
+extern "C" int dibs_log_joint_prob(dibs_plan* p, const float* g, const float* theta, int32_t n, int32_t n_samples,
+                                   float* lp_out, void* stream_) {
+    if (!p || !g || !lp_out || n < 1 || n_samples < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_log_joint_prob: bad arguments");
+    if (!p->has_data) return fail(DIBS_ERR_STATE, "dibs_set_data has not been called");
+    if (p->Dth && !theta) return fail(DIBS_ERR_INVALID_ARG, "theta required");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Scratch sc;
+    float* zdummy;
+    TRY(sc.get(&zdummy, (size_t)n * p->Dz));
+    CU(cudaMemsetAsync(zdummy, 0, (size_t)n * p->Dz * sizeof(float), stream));
+    Src s{zdummy, p->Dz, theta, p->Dth, n, 0, nullptr, nullptr, 0};
+    McParams q;
+    fill_mc(p, s, q);
+    q.n_samples = n_samples; q.g_ext = g; q.lp_out = lp_out;
+    q.gpb = p->gpb_z < n_samples ? p->gpb_z : n_samples; q.n_chunks = 1; q.s_per_chunk = n_samples;
+    TRY(launch_mc<MC_LP_ONLY>(p, q, stream));
+    CU(cudaStreamSynchronize(stream));
+    return DIBS_OK;
+}
+
+static int hook_grads(dibs_plan* p, const float* z, const float* theta, const float* baselines, int t,
+                      const uint32_t* keys, int n, int what /*0 z-lik, 1 theta, 2 prior, 3 constraint only*/,
+                      float* grad_out, float* baselines_out, cudaStream_t stream) {
+    if (!p->has_data && what < 2) return fail(DIBS_ERR_STATE, "dibs_set_data has not been called");
+    Scratch sc;
+    Src s{z, p->Dz, theta, p->Dth, n, 0, nullptr, keys, t};
+    int chunks, spc;
+    const int gpb = p->gpb_z;
+    choose_chunks(p->cfg.n_grad_mc_samples, gpb, n, &chunks, &spc);
+    float *acc = nullptr, *stats = nullptr, *acyc = nullptr, *gz_tmp = nullptr;
+    AsmParams a;
+    fill_asm(p, s, a);
+    McParams q;
+    fill_mc(p, s, q);
+    q.n_chunks = chunks; q.s_per_chunk = spc; q.gpb = gpb;
+    if (what == 0) {
+        TRY(sc.get(&acc, (size_t)n * chunks * p->d * p->d));
+        TRY(sc.get(&stats, (size_t)n * chunks * 4));
+        q.pre_split = 1; q.part_acc = acc; q.acc_size = p->d * p->d; q.part_stats = stats;
+        if (p->cfg.grad_estimator_z == DIBS_ESTIMATOR_SCORE) TRY(launch_mc<MC_Z_SCORE>(p, q, stream));
+        else TRY(launch_mc<MC_Z_REPARAM>(p, q, stream));
+        a.zacc = acc; a.zstats = stats; a.z_chunks = chunks; a.baselines_in = baselines; a.baselines_out = baselines_out;
+        a.grad_z = grad_out; a.gz_ld = p->Dz;
+    } else if (what == 1) {
+        if (!p->Dth) return fail(DIBS_ERR_INVALID_ARG, "no theta in marginal inference");
+        TRY(sc.get(&acc, (size_t)n * chunks * p->Dth));
+        TRY(sc.get(&stats, (size_t)n * chunks * 4));
+        TRY(sc.get(&gz_tmp, (size_t)n * p->Dz));
+        q.pre_split = 0; q.part_acc = acc; q.acc_size = p->Dth; q.part_stats = stats;
+        TRY(launch_mc<MC_THETA_HARD>(p, q, stream));
+        a.thacc = acc; a.thstats = stats; a.th_chunks = chunks; a.th_dim = p->Dth;
+        a.grad_z = gz_tmp; a.gz_ld = p->Dz; a.grad_th = grad_out; a.gth_ld = p->Dth;
+    } else {
+        TRY(sc.get(&acyc, (size_t)n * p->d * p->d));
+        TRY(launch_acyc(p, s, 0, acyc, stream));
+        a.acyc = acyc; a.constraint_only = (what == 3);
+        a.grad_z = grad_out; a.gz_ld = p->Dz;
+    }
+    TRY(launch_asm(p, a, stream));
+    CU(cudaStreamSynchronize(stream));
+    return DIBS_OK;
+}
+
+extern "C" int dibs_grad_z_likelihood(dibs_plan* p, const float* z, const float* theta, const float* baselines, int32_t t,
+                                      const uint32_t* keys, int32_t n, float* grad_out, float* baselines_out, void* stream) {
+    if (!p || !z || !keys || !grad_out || n < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_grad_z_likelihood: bad arguments");
+    if (p->Dth && !theta) return fail(DIBS_ERR_INVALID_ARG, "theta required");
+    return hook_grads(p, z, theta, baselines, t, keys, n, 0, grad_out, baselines_out, (cudaStream_t)stream);
+}
+
+extern "C" int dibs_grad_theta_likelihood(dibs_plan* p, const float* z, const float* theta, int32_t t, const uint32_t* keys,
+                                          int32_t n, float* grad_out, void* stream) {
+    if (!p || !z || !theta || !keys || !grad_out || n < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_grad_theta_likelihood: bad arguments");
+    return hook_grads(p, z, theta, nullptr, t, keys, n, 1, grad_out, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int dibs_grad_latent_prior(dibs_plan* p, const float* z, int32_t t, const uint32_t* keys, int32_t n,
+                                      int32_t constraint_only, float* grad_out, void* stream) {
+    if (!p || !z || !keys || !grad_out || n < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_grad_latent_prior: bad arguments");
+    return hook_grads(p, z, nullptr, nullptr, t, keys, n, constraint_only ? 3 : 2, grad_out, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int dibs_acyclic_constr(dibs_plan* p, const float* g, int32_t n, float* h_out, void* stream_) {
+    if (!p || !g || !h_out || n < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_acyclic_constr: bad arguments");
+    size_t smem = (size_t)4 * p->d * (p->d | 1) * sizeof(float);
+    TRY(set_smem(k_acyclic_value, smem));
+    k_acyclic_value<<<n, 256, smem, (cudaStream_t)stream_>>>(g, n, p->d, h_out);
+    LAUNCHED();
+    return DIBS_OK;
+}
+
+static int hook_pair(dibs_plan* p, const float* z, const float* theta, const float* gz, const float* gth, int n,
+                     float* k_out, float* phi_z, float* phi_th, cudaStream_t stream) {
+    Scratch sc;
+    const int D = p->D;
+    float *xs, *gs, *dist, *kz, *kt, *kf, *phi = nullptr;
+    TRY(sc.get(&xs, (size_t)n * D));
+    TRY(sc.get(&gs, (size_t)n * D));
+    const size_t fz = sizeof(float) * p->Dz, ft = sizeof(float) * p->Dth, fd = sizeof(float) * D;
+    CU(cudaMemsetAsync(gs, 0, (size_t)n * fd, stream));
+    CU(cudaMemcpy2DAsync(xs, fd, z, fz, fz, n, cudaMemcpyDeviceToDevice, stream));
+    if (p->Dth) CU(cudaMemcpy2DAsync(xs + p->Dz, fd, theta, ft, ft, n, cudaMemcpyDeviceToDevice, stream));
+    if (gz) CU(cudaMemcpy2DAsync(gs, fd, gz, fz, fz, n, cudaMemcpyDeviceToDevice, stream));
+    if (gth && p->Dth) CU(cudaMemcpy2DAsync(gs + p->Dz, fd, gth, ft, ft, n, cudaMemcpyDeviceToDevice, stream));
+    PairParams q;
+    fill_pair(p, q);
+    q.n_all = n; q.row0 = 0; q.n_rows = n;
+    int ns = p->n_split, sl = p->split_len;
+    size_t plane = (size_t)n * n;
+    TRY(sc.get(&dist, plane * 2 * ns));
+    TRY(sc.get(&kz, plane)); TRY(sc.get(&kt, plane));
+    if (!k_out) TRY(sc.get(&kf, plane)); else kf = k_out;
+    q.n_split = ns; q.split_len = sl; q.dist_part = dist; q.kz = kz; q.kt = p->Dth ? kt : nullptr; q.kfull = kf;
+    q.x_all = xs; q.ld = D; q.g_all = gs; q.g_ld = D;
+    if (phi_z) { TRY(sc.get(&phi, (size_t)n * D)); q.phi_out = phi; q.phi_ld = D; }
+    TRY(launch_pair(q, phi_z != nullptr, stream));
+    if (phi_z) {
+        CU(cudaMemcpy2DAsync(phi_z, fz, phi, fd, fz, n, cudaMemcpyDeviceToDevice, stream));
+        if (phi_th && p->Dth) CU(cudaMemcpy2DAsync(phi_th, ft, phi + p->Dz, fd, ft, n, cudaMemcpyDeviceToDevice, stream));
+    }
+    CU(cudaStreamSynchronize(stream));
+    return DIBS_OK;
+}
+
+extern "C" int dibs_kernel_matrix(dibs_plan* p, const float* z, const float* theta, int32_t n, float* k_out, void* stream) {
+    if (!p || !z || !k_out || n < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_kernel_matrix: bad arguments");
+    if (p->Dth && !theta) return fail(DIBS_ERR_INVALID_ARG, "theta required");
+    return hook_pair(p, z, theta, nullptr, nullptr, n, k_out, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int dibs_svgd_phi(dibs_plan* p, const float* z, const float* theta, const float* grad_z, const float* grad_theta,
+                             int32_t n, float* phi_z_out, float* phi_theta_out, void* stream) {
+    if (!p || !z || !grad_z || !phi_z_out || n < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_svgd_phi: bad arguments");
+    if (p->Dth && (!theta || !grad_theta || !phi_theta_out)) return fail(DIBS_ERR_INVALID_ARG, "theta arguments required");
+    return hook_pair(p, z, theta, grad_z, grad_theta, n, nullptr, phi_z_out, phi_theta_out, (cudaStream_t)stream);
+}
+
+// host-side key arithmetic for the Python layer (random.split before the jit boundary, svgd.py:294,751)
+extern "C" int dibs_prng_split(const uint32_t* key_host, int32_t num, int32_t partitionable, uint32_t* out_host) {
+    if (!key_host || !out_host || num < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_prng_split: bad arguments");
+    const uint2 key = make_uint2(key_host[0], key_host[1]);
+    for (int r = 0; r < num; ++r) {
+        uint2 row = jax_split_row(key, (uint32_t)r, (uint32_t)num, partitionable != 0);
+        out_host[2 * r] = row.x; out_host[2 * r + 1] = row.y;
+    }
+    return DIBS_OK;
+}

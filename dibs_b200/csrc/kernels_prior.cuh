@@ -1,0 +1,351 @@
+// Latent prior score: acyclicity-constraint power series over Gumbel-soft graphs, graph prior through the
+// edge probabilities, Gaussian prior on Z; plus the per-particle "assemble" step that merges the MC-pass
+// partials and applies the chain rule through S = U V^T once.
+//
+// replaces: dibs/inference/dibs.py:557-658 (constraint_gumbel, grad_constraint_gumbel,
+// log_graph_prior_particle, eltwise_grad_latent_prior), dibs/graph_utils.py:8-28 (acyclic_constr_nograd),
+// dibs/models/graph.py:93-108,182-196,263-276 (unnormalized_log_prob_soft), and the final reshapes of
+// dibs.py:376-385,451-457,531-549.
+#pragma once
+#include "common.cuh"
+
+namespace dibs {
+
+struct AcycParams {
+    const float* z; int z_ld;
+    int n_local, m_offset, n_particles;
+    int d, k, n_samples;                 // A
+    const StepState* st; int which_split; int partitionable;
+    const uint32_t* keys_override; int t_override;
+    float alpha_linear, tau;
+    float* ds_out;                       // [n_local][d*d]: sum over samples of dh/dS (before the 1/A mean)
+};
+
+// C = A * B for d x d row-major matrices with leading dimension ld, cooperatively by a group of threads.
+__device__ __forceinline__ void group_matmul(const float* __restrict__ A, const float* __restrict__ B,
+                                             float* __restrict__ C, int d, int ld, int lane, int gsize) {
+    for (int e = lane; e < d * d; e += gsize) {
+        int i = e / d, j = e % d;
+        float acc = 0.0f;
+        for (int kk = 0; kk < d; ++kk) acc = fmaf(A[i * ld + kk], B[kk * ld + j], acc);
+        C[i * ld + j] = acc;
+    }
+}
+
+// One group (a warp when WARP_GROUP, else the whole CTA) handles one soft-graph sample at a time:
+// G = sigmoid(tau (eps + alpha S)); E = (I + G/d)^(d-1); dS += E^T o tau alpha G (1-G)   
+template <bool WARP_GROUP>
+__global__ void __launch_bounds__(256) k_acyclic_grad(AcycParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int d = p.d, k = p.k, ld = d | 1;   // odd leading dimension: conflict-free column walks
+    const int m = blockIdx.x, tid = threadIdx.x;
+    const int t = p.st ? p.st->t : p.t_override;
+    const float alpha = p.alpha_linear * (float)t;
+    const int n_groups = WARP_GROUP ? (blockDim.x >> 5) : 1;
+    const int grp = WARP_GROUP ? (tid >> 5) : 0;
+    const int lane = WARP_GROUP ? (tid & 31) : tid;
+    const int gsize = WARP_GROUP ? 32 : blockDim.x;
+    const int mat = d * ld;
+
+    float* sS = smem;                               // [d*d] alpha * scores
+    float* sZ = sS + d * d;                         // [2*d*k]
+    float* gbase = sZ + 2 * d * k + (size_t)grp * 6 * mat;
+    float* bG = gbase;                              // soft graph
+    float* bZ0 = gbase + mat;                       // running square
+    float* bZ1 = gbase + 2 * mat;
+    float* bR0 = gbase + 3 * mat;                   // running result
+    float* bR1 = gbase + 4 * mat;
+    float* bAcc = gbase + 5 * mat;                  // per-group accumulator of dS
+
+    const float* zrow = p.z + (size_t)m * p.z_ld;
+    for (int e = tid; e < 2 * d * k; e += blockDim.x) sZ[e] = zrow[e];
+    __syncthreads();
+    for (int e = tid; e < d * d; e += blockDim.x) {
+        int i = e / d, j = e % d;
+        float acc = 0.0f;
+        for (int kk = 0; kk < k; ++kk) acc = fmaf(sZ[(i * k + kk) * 2], sZ[(j * k + kk) * 2 + 1], acc);
+        sS[e] = alpha * acc;
+    }
+    for (int e = lane; e < mat; e += gsize) bAcc[e] = 0.0f;
+    uint2 key;
+    if (p.keys_override) key = make_uint2(p.keys_override[2 * m], p.keys_override[2 * m + 1]);
+    else key = step_particle_key(p.st, p.which_split, (uint32_t)(p.m_offset + m), (uint32_t)p.n_particles, p.partitionable);
+    __syncthreads();
+
+    const float inv_d = 1.0f / (float)d;
+    const uint32_t n_total = (uint32_t)p.n_samples * d * d;
+    for (int a = grp; a < p.n_samples; a += n_groups) {
+        // soft graph and M = I + G/d  (graph_utils.py:22-25)
+        for (int e = lane; e < d * d; e += gsize) {
+            int i = e / d, j = e % d;
+            float g = 0.0f;
+            if (i != j) {
+                uint32_t bits = jax_bits(key, (uint32_t)a * d * d + e, n_total, p.partitionable);
+                g = sigmoidf_ref(p.tau * (logistic_from_bits(bits) + sS[e]));
+            }
+            bG[i * ld + j] = g;
+            bZ0[i * ld + j] = (i == j ? 1.0f : 0.0f) + inv_d * g;
+        }
+        if (WARP_GROUP) __syncwarp(); else __syncthreads();
+        // E = M^(d-1) by binary exponentiation (LSB first, like jnp.linalg.matrix_power)
+        float* zc = bZ0; float* zn = bZ1; float* rc = nullptr; float* rn = bR0;
+        int n = d - 1;
+        while (n > 0) {
+            if (n & 1) {
+                if (rc == nullptr) {
+                    for (int e = lane; e < mat; e += gsize) rn[e] = zc[e];
+                } else {
+                    group_matmul(rc, zc, rn, d, ld, lane, gsize);
+                }
+                float* tmp = rc; rc = rn; rn = (tmp == nullptr) ? bR1 : tmp;
+                if (WARP_GROUP) __syncwarp(); else __syncthreads();
+            }
+            n >>= 1;
+            if (n > 0) {
+                group_matmul(zc, zc, zn, d, ld, lane, gsize);
+                float* tmp = zc; zc = zn; zn = tmp;
+                if (WARP_GROUP) __syncwarp(); else __syncthreads();
+            }
+        }
+        // dh/dG = E^T (d * (1/d) = 1); through the sigmoid: tau * alpha * g (1 - g); diagonal is masked
+        for (int e = lane; e < d * d; e += gsize) {
+            int i = e / d, j = e % d;
+            float g = bG[i * ld + j];
+            float e_t = (d == 1) ? 1.0f : rc[j * ld + i];
+            if (i != j) bAcc[i * ld + j] += e_t * (p.tau * alpha) * g * (1.0f - g);
+        }
+        if (WARP_GROUP) __syncwarp(); else __syncthreads();
+    }
+    __syncthreads();
+    float* out = p.ds_out + (size_t)m * d * d;
+    for (int e = tid; e < d * d; e += blockDim.x) {
+        int i = e / d, j = e % d;
+        float sum = 0.0f;
+        for (int g = 0; g < n_groups; ++g) sum += smem[d * d + 2 * d * k + (size_t)g * 6 * mat + 5 * mat + i * ld + j];
+        out[e] = sum;
+    }
+}
+
+inline size_t acyclic_smem(int d, int k, int n_groups) {
+    return ((size_t)d * d + 2 * (size_t)d * k + (size_t)n_groups * 6 * d * (d | 1)) * sizeof(float);
+}
+
+// h(G) = tr((I + G/d)^d) - d for caller-supplied graphs (hook for graph_utils.py:8-28); one CTA per graph.
+__global__ void __launch_bounds__(256) k_acyclic_value(const float* g, int n, int d, float* h_out) {
+    extern __shared__ __align__(16) float smem[];
+    const int ld = d | 1, mat = d * ld, tid = threadIdx.x;
+    float* bZ0 = smem; float* bZ1 = smem + mat; float* bR0 = smem + 2 * mat; float* bR1 = smem + 3 * mat;
+    const float* gm = g + (size_t)blockIdx.x * d * d;
+    const float inv_d = 1.0f / (float)d;
+    for (int e = tid; e < d * d; e += blockDim.x) {
+        int i = e / d, j = e % d;
+        bZ0[i * ld + j] = (i == j ? 1.0f : 0.0f) + inv_d * gm[e];
+    }
+    __syncthreads();
+    float* zc = bZ0; float* zn = bZ1; float* rc = nullptr; float* rn = bR0;
+    int nn = d;
+    while (nn > 0) {
+        if (nn & 1) {
+            if (rc == nullptr) { for (int e = tid; e < mat; e += blockDim.x) rn[e] = zc[e]; }
+            else group_matmul(rc, zc, rn, d, ld, tid, blockDim.x);
+            float* tmp = rc; rc = rn; rn = (tmp == nullptr) ? bR1 : tmp;
+            __syncthreads();
+        }
+        nn >>= 1;
+        if (nn > 0) {
+            group_matmul(zc, zc, zn, d, ld, tid, blockDim.x);
+            float* tmp = zc; zc = zn; zn = tmp;
+            __syncthreads();
+        }
+    }
+    if (tid < 32) {
+        float tr = 0.0f;
+        for (int i = tid; i < d; i += 32) tr += rc[i * ld + i];
+        tr = warp_sum(tr);
+        if (tid == 0) h_out[blockIdx.x] = tr - (float)d;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// assemble: partials -> d log p / dZ (and d/dTheta) for one particle
+// ------------------------------------------------------------------------------------------
+struct AsmParams {
+    const float* z; int z_ld;
+    int n_local, d, k;
+    const StepState* st; int t_override;
+    float alpha_linear, beta_linear;
+    // Z-likelihood partials
+    const float* zacc; const float* zstats; int z_chunks; int z_mode;   // MC_Z_SCORE / MC_Z_REPARAM; zacc null = skip
+    int n_samples;
+    float sf_coef;                        // score_function_baseline
+    const float* baselines_in; float* baselines_out;
+    // theta partials
+    const float* thacc; const float* thstats; int th_chunks; int th_dim;
+    // prior
+    const float* acyc; int n_acyc;        // [n_local][d*d] sums over A samples; null = skip prior terms entirely
+    int constraint_only;                  // hook: return mean_a grad h alone (no beta, no other terms)
+    int prior_kind; float er_coef;        // log p - log(1-p)
+    float sigma_z2;                       // latent_prior_std ** 2
+    float* grad_z; int gz_ld;
+    float* grad_th; int gth_ld;
+};
+
+__device__ __forceinline__ void merge_stats(const float* stats, int chunks, float& mx, float& l, float& sum_lp) {
+    mx = -INFINITY;
+    for (int c = 0; c < chunks; ++c) mx = fmaxf(mx, stats[c * 4]);
+    l = 0.0f; sum_lp = 0.0f;
+    for (int c = 0; c < chunks; ++c) {
+        float mc = stats[c * 4];
+        if (mc != -INFINITY) l += stats[c * 4 + 1] * expf(mc - mx);
+        sum_lp += stats[c * 4 + 2];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_assemble_grad(AsmParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int d = p.d, k = p.k, tid = threadIdx.x, m = blockIdx.x;
+    const int t = p.st ? p.st->t : p.t_override;
+    const float alpha = p.alpha_linear * (float)t;
+    const float beta = p.beta_linear * (float)t;
+    float* sZ = smem;                 // [2dk]
+    float* sP = sZ + 2 * d * k;       // [d*d]
+    float* sDS = sP + d * d;          // [d*d]
+    float* sCol = sDS + d * d;        // [d]
+
+    const float* zrow = p.z + (size_t)m * p.z_ld;
+    for (int e = tid; e < 2 * d * k; e += blockDim.x) sZ[e] = zrow[e];
+    __syncthreads();
+    for (int e = tid; e < d * d; e += blockDim.x) {
+        int i = e / d, j = e % d;
+        float acc = 0.0f;
+        for (int kk = 0; kk < k; ++kk) acc = fmaf(sZ[(i * k + kk) * 2], sZ[(j * k + kk) * 2 + 1], acc);
+        sP[e] = (i == j) ? 0.0f : sigmoidf_ref(alpha * acc);
+    }
+    __syncthreads();
+    if (p.acyc && !p.constraint_only && p.prior_kind == 1 && tid < d) {
+        float indeg = 0.0f;
+        for (int i = 0; i < d; ++i) indeg += sP[i * d + tid];        // soft_g.sum(0)  (graph.py:195)
+        sCol[tid] = -3.0f / (1.0f + indeg);
+    }
+    // likelihood partial merge (uniform per CTA)
+    float zmx = 0.0f, zl = 1.0f, zsum = 0.0f, base_fac = 1.0f;
+    if (p.zacc) {
+        merge_stats(p.zstats + (size_t)m * p.z_chunks * 4, p.z_chunks, zmx, zl, zsum);
+        if (p.z_mode == MC_Z_SCORE && p.sf_coef > 0.0f) base_fac = expf(-p.baselines_in[m]);
+    }
+    __syncthreads();
+    for (int e = tid; e < d * d; e += blockDim.x) {
+        int i = e / d, j = e % d;
+        float ds = 0.0f;
+        if (i != j) {
+            float pe = sP[e];
+            if (p.zacc) {
+                float num = 0.0f;
+                for (int c = 0; c < p.z_chunks; ++c) {
+                    float mc = p.zstats[((size_t)m * p.z_chunks + c) * 4];
+                    if (mc != -INFINITY) num += p.zacc[((size_t)m * p.z_chunks + c) * d * d + e] * expf(mc - zmx);
+                }
+                float w = num / zl;
+                // score: e^{-b} alpha (Gbar - P) (App. B-1/2; dibs.py:363-382); reparam: softmax-weighted dS
+                ds += (p.z_mode == MC_Z_SCORE) ? base_fac * alpha * (w - pe) : w;
+            }
+            if (p.acyc) {
+                float ac = p.acyc[(size_t)m * d * d + e] / (float)p.n_acyc;    // .mean(0)  (dibs.py:601)
+                if (p.constraint_only) ds += ac;
+                else {
+                    ds -= beta * ac;
+                    float coef = p.prior_kind == 0 ? p.er_coef : (p.prior_kind == 1 ? sCol[j] : 0.0f);
+                    ds += coef * alpha * pe * (1.0f - pe);                      // App. B-5
+                }
+            }
+        }
+        sDS[e] = ds;
+    }
+    __syncthreads();
+    // chain rule through S = U V^T: dU = dS V, dV = dS^T U; Gaussian prior -Z/sigma^2 (dibs.py:657)
+    float* gz = p.grad_z + (size_t)m * p.gz_ld;
+    const bool gauss = p.acyc && !p.constraint_only;
+    for (int e = tid; e < d * k; e += blockDim.x) {
+        int i = e / k, kk = e % k;
+        float du = 0.0f, dv = 0.0f;
+        for (int j = 0; j < d; ++j) {
+            du = fmaf(sDS[i * d + j], sZ[(j * k + kk) * 2 + 1], du);
+            dv = fmaf(sDS[j * d + i], sZ[(j * k + kk) * 2], dv);
+        }
+        if (gauss) {
+            du -= sZ[2 * e] / p.sigma_z2;
+            dv -= sZ[2 * e + 1] / p.sigma_z2;
+        }
+        gz[2 * e] = du; gz[2 * e + 1] = dv;
+    }
+    if (p.zacc && p.baselines_out && tid == 0) {
+        float b_in = p.baselines_in ? p.baselines_in[m] : 0.0f;
+        // dibs.py:388-389 (only the score estimator touches the baseline)
+        p.baselines_out[m] = (p.z_mode == MC_Z_SCORE)
+            ? p.sf_coef * (zsum / (float)p.n_samples) + (1.0f - p.sf_coef) * b_in : b_in;
+    }
+    if (p.thacc) {
+        float tmx, tl, tsum;
+        merge_stats(p.thstats + (size_t)m * p.th_chunks * 4, p.th_chunks, tmx, tl, tsum);
+        float* gth = p.grad_th + (size_t)m * p.gth_ld;
+        for (int e = tid; e < p.th_dim; e += blockDim.x) {
+            float num = 0.0f;
+            for (int c = 0; c < p.th_chunks; ++c) {
+                float mc = p.thstats[((size_t)m * p.th_chunks + c) * 4];
+                if (mc != -INFINITY) num += p.thacc[((size_t)m * p.th_chunks + c) * p.th_dim + e] * expf(mc - tmx);
+            }
+            gth[e] = num / tl;
+        }
+    }
+}
+
+inline size_t assemble_smem(int d, int k) { return ((size_t)2 * d * k + 2 * (size_t)d * d + d) * sizeof(float); }
+
+// edge_probs / particle_to_g_lim hooks (dibs.py:84-99,168-184); one CTA per particle
+__global__ void __launch_bounds__(256) k_edge_probs(const float* z, int z_ld, int d, int k, float alpha,
+                                                    float* p_out, int32_t* g_lim_out) {
+    extern __shared__ __align__(16) float smem[];
+    const float* zrow = z + (size_t)blockIdx.x * z_ld;
+    for (int e = threadIdx.x; e < 2 * d * k; e += blockDim.x) smem[e] = zrow[e];
+    __syncthreads();
+    for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+        int i = e / d, j = e % d;
+        float acc = 0.0f;
+        for (int kk = 0; kk < k; ++kk) acc = fmaf(smem[(i * k + kk) * 2], smem[(j * k + kk) * 2 + 1], acc);
+        if (p_out) p_out[(size_t)blockIdx.x * d * d + e] = (i == j) ? 0.0f : sigmoidf_ref(alpha * acc);
+        if (g_lim_out) g_lim_out[(size_t)blockIdx.x * d * d + e] = (i != j && acc > 0.0f) ? 1 : 0;
+    }
+}
+
+// sample_g / soft-graph hooks: materialise the graphs the fused kernels generate on the fly
+__global__ void __launch_bounds__(256) k_sample_graphs(const float* p_or_z, int ld, const uint32_t* keys, int d, int k,
+                                                       int n_samples, int hard, float alpha, float tau,
+                                                       int partitionable, int32_t* g_hard, float* g_soft) {
+    extern __shared__ __align__(16) float smem[];
+    const int m = blockIdx.x, tid = threadIdx.x;
+    float* sA = smem; float* sZ = smem + d * d;
+    if (hard) {
+        for (int e = tid; e < d * d; e += blockDim.x) sA[e] = p_or_z[(size_t)m * ld + e];
+    } else {
+        const float* zrow = p_or_z + (size_t)m * ld;
+        for (int e = tid; e < 2 * d * k; e += blockDim.x) sZ[e] = zrow[e];
+        __syncthreads();
+        for (int e = tid; e < d * d; e += blockDim.x) {
+            int i = e / d, j = e % d;
+            float acc = 0.0f;
+            for (int kk = 0; kk < k; ++kk) acc = fmaf(sZ[(i * k + kk) * 2], sZ[(j * k + kk) * 2 + 1], acc);
+            sA[e] = alpha * acc;
+        }
+    }
+    __syncthreads();
+    const uint2 key = make_uint2(keys[2 * m], keys[2 * m + 1]);
+    const uint32_t n_total = (uint32_t)n_samples * d * d;
+    for (uint32_t e = tid; e < n_total; e += blockDim.x) {
+        int ij = e % (d * d), i = ij / d, j = ij % d;
+        uint32_t bits = jax_bits(key, e, n_total, partitionable);
+        if (hard) g_hard[(size_t)m * n_total + e] = (i != j && bits_to_unit(bits) < sA[ij]) ? 1 : 0;
+        else g_soft[(size_t)m * n_total + e] = (i == j) ? 0.0f : sigmoidf_ref(tau * (logistic_from_bits(bits) + sA[ij]));
+    }
+}
+
+}  // namespace dibs

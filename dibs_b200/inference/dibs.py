@@ -1,0 +1,345 @@
+"""Host-side mirror of the reference's ``DiBS`` backbone (dibs/inference/dibs.py:12-658).
+
+Every method keeps the reference's name, argument meaning and batching (``eltwise_*`` = batched over
+particles) but dispatches to the CUDA kernels through the C ABI (dibs_b200/_native.py); there is no
+Python/PyTorch implementation of the math and no fallback.  Arrays are torch CUDA tensors:
+
+  z       float32 [..., d, k, 2]      theta   the likelihood model's pytree (or its flat [M, Dtheta] form)
+  keys    uint32 bit patterns [.., 2] (any integer dtype / numpy / torch accepted)
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _native as nat
+
+
+def as_key(key):
+    """-> numpy uint32[2] (JAX ``PRNGKey`` bit pattern)."""
+    if isinstance(key, torch.Tensor):
+        key = key.detach().cpu().numpy()
+    key = np.asarray(key)
+    if key.dtype.kind == "i":
+        key = key.astype(np.int64) & 0xFFFFFFFF
+    return np.ascontiguousarray(key.astype(np.uint32))
+
+
+def PRNGKey(seed):
+    """``jax.random.PRNGKey``: uint32[2] = [seed >> 32, seed & 0xffffffff]."""
+    seed = int(seed)
+    return np.array([(seed >> 32) & 0xFFFFFFFF, seed & 0xFFFFFFFF], dtype=np.uint32)
+
+
+def split(key, num=2, partitionable=False):
+    """``jax.random.split`` on the host (key handling outside the step loop, svgd.py:294,751)."""
+    key = as_key(key)
+    out = np.zeros((num, 2), np.uint32)
+    nat.check(nat.lib().dibs_prng_split(nat.ptr(key), num, int(partitionable), nat.ptr(out)))
+    return out
+
+
+def keys_to_device(keys, device):
+    keys = as_key(keys)
+    return torch.from_numpy(keys.view(np.int32).copy()).to(device)
+
+
+def keys_from_device(t):
+    return t.detach().cpu().numpy().view(np.uint32).copy()
+
+
+class DiBS:
+    """Backbone shared by :class:`MarginalDiBS` and :class:`JointDiBS` (reference: dibs/inference/dibs.py:12-78)."""
+
+    def __init__(self, *, x, interv_mask, graph_model, likelihood_model, joint, kernel_obj, optimizer, optimizer_param,
+                 alpha_linear, beta_linear, tau, n_grad_mc_samples, n_acyclicity_mc_samples, grad_estimator_z,
+                 score_function_baseline, latent_prior_std, verbose, device=None, prng_partitionable=False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dibs_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.x = torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x).to(self.device, torch.float32).contiguous()
+        if interv_mask is None:
+            self.interv_mask = None
+        else:
+            im = interv_mask if isinstance(interv_mask, torch.Tensor) else torch.as_tensor(np.asarray(interv_mask))
+            self.interv_mask = im.to(self.device, torch.int32).contiguous()
+        self.n_vars = self.x.shape[-1]
+        self.graph_model = graph_model
+        self.likelihood_model = likelihood_model
+        self.joint = joint
+        self.kernel = kernel_obj
+        if optimizer not in nat.OPTIMIZER:
+            raise ValueError()                      # svgd.py:121-122
+        self.optimizer = optimizer
+        self.optimizer_param = optimizer_param
+        self.alpha_linear = alpha_linear
+        self.beta_linear = beta_linear
+        self.alpha = lambda t: (alpha_linear * t)
+        self.beta = lambda t: (beta_linear * t)
+        self.tau = tau
+        self.n_grad_mc_samples = n_grad_mc_samples
+        self.n_acyclicity_mc_samples = n_acyclicity_mc_samples
+        self.grad_estimator_z = grad_estimator_z
+        self.score_function_baseline = score_function_baseline
+        self.latent_prior_std = latent_prior_std
+        self.verbose = verbose
+        self.prng_partitionable = prng_partitionable
+        for obj, what in ((graph_model, "graph_model"), (likelihood_model, "likelihood_model")):
+            if not hasattr(obj, "native_kind"):
+                raise NotImplementedError(f"{what} {type(obj).__name__} has no native implementation in dibs_b200")
+        if hasattr(likelihood_model, "check_native"):
+            likelihood_model.check_native()
+        self._plans = {}
+
+    # ------------------------------------------------------------------ plan management
+    def _dist(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(), dist.get_rank()
+        return 1, 0
+
+    def _std(self, n_dim):
+        if self.latent_prior_std:
+            return float(self.latent_prior_std)
+        return float(np.float32(1.0) / np.sqrt(np.float32(n_dim)))   # svgd.py:142,302 in fp32
+
+    def _plan(self, n_particles, n_dim=None, sharded=False):
+        """Native plan for (M, k); ``sharded`` plans split particles over the torch.distributed ranks."""
+        n_dim = n_dim or self.n_vars
+        world, rank = self._dist() if sharded else (1, 0)
+        k = (int(n_particles), int(n_dim), world, rank)
+        if k in self._plans:
+            return self._plans[k]
+        if self.grad_estimator_z not in nat.ESTIMATOR:
+            raise ValueError(f'Unknown gradient estimator `{self.grad_estimator_z}`')     # dibs.py:318
+        lm, gm = self.likelihood_model, self.graph_model
+        c = nat.DibsConfig()
+        c.n_vars, c.n_dim, c.n_particles = self.n_vars, n_dim, n_particles
+        c.joint = int(self.joint)
+        c.likelihood = nat.LIK[lm.native_kind]
+        c.graph_prior = nat.PRIOR[gm.native_kind]
+        c.grad_estimator_z = nat.ESTIMATOR[self.grad_estimator_z]
+        c.optimizer = nat.OPTIMIZER[self.optimizer]
+        c.n_grad_mc_samples = self.n_grad_mc_samples
+        c.n_acyclicity_mc_samples = self.n_acyclicity_mc_samples
+        c.hidden = getattr(lm, "hidden", 0) if lm.native_kind == "densenn" else 0
+        c.prng_partitionable = int(self.prng_partitionable)
+        c.alpha_linear, c.beta_linear, c.tau = self.alpha_linear, self.beta_linear, self.tau
+        c.score_function_baseline = self.score_function_baseline
+        c.latent_prior_std = self._std(n_dim)
+        kn = self.kernel
+        c.h_latent = getattr(kn, "h_latent", getattr(kn, "h", 5.0))
+        c.h_theta = getattr(kn, "h_theta", 500.0)
+        c.scale_latent = getattr(kn, "scale_latent", getattr(kn, "scale", 1.0))
+        c.scale_theta = getattr(kn, "scale_theta", 1.0)
+        c.stepsize = self.optimizer_param["stepsize"]
+        c.er_p = getattr(gm, "p", 0.0)
+        c.obs_noise = getattr(lm, "obs_noise", 0.1)
+        c.mean_edge = getattr(lm, "mean_edge", 0.0)
+        c.sig_edge = getattr(lm, "sig_edge", 1.0)
+        c.min_edge = getattr(lm, "min_edge", 0.5)
+        c.sig_param = getattr(lm, "sig_param", 1.0)
+        c.bge_alpha_mu = getattr(lm, "alpha_mu", 1.0)
+        c.bge_alpha_lambd = getattr(lm, "alpha_lambd", self.n_vars + 2)
+        c.world_size, c.rank = world, rank
+        handle = ctypes.c_void_p()
+        nat.check(nat.lib().dibs_plan_create(ctypes.byref(c), ctypes.byref(handle)))
+        plan = _Plan(handle, c, self)
+        mean_obs = getattr(lm, "mean_obs", None)
+        mean_np = None if mean_obs is None else np.ascontiguousarray(np.asarray(mean_obs, np.float32))
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().dibs_set_data(handle, nat.ptr(self.x), nat.ptr(self.interv_mask), self.x.shape[0],
+                                              nat.ptr(mean_np), self._stream()))
+        if world > 1:
+            plan.attach_nccl()
+        self._plans[k] = plan
+        return plan
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _f32(self, t):
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(np.asarray(t))
+        return t.to(self.device, torch.float32).contiguous()
+
+    def _flat_theta(self, theta):
+        if theta is None:
+            return None
+        if isinstance(theta, torch.Tensor) and theta.dim() == 2 and theta.shape[1] == self.likelihood_model.theta_dim():
+            return self._f32(theta)
+        return self._f32(self.likelihood_model.flatten(theta))
+
+    # ------------------------------------------------------------------ backbone functionality (dibs.py:84-184)
+    def particle_to_g_lim(self, z):
+        """G for alpha = infinity: (U V^T > 0), zero diagonal (dibs.py:84-99).  z [..., d, k, 2] -> int32 [..., d, d]."""
+        z = self._f32(z)
+        lead, (d, k) = z.shape[:-3], z.shape[-3:-1]
+        n = int(np.prod(lead)) if lead else 1
+        out = torch.empty((n, d, d), dtype=torch.int32, device=self.device)
+        plan = self._plan(max(n, 1), k)
+        nat.check(nat.lib().dibs_particle_to_g_lim(plan.handle, nat.ptr(z), n, nat.ptr(out), self._stream()))
+        return out.reshape(*lead, d, d)
+
+    def edge_probs(self, z, t):
+        """sigmoid(alpha(t) U V^T), zero diagonal (dibs.py:168-184)."""
+        z = self._f32(z)
+        lead, (d, k) = z.shape[:-3], z.shape[-3:-1]
+        n = int(np.prod(lead)) if lead else 1
+        out = torch.empty((n, d, d), dtype=torch.float32, device=self.device)
+        plan = self._plan(max(n, 1), k)
+        nat.check(nat.lib().dibs_edge_probs(plan.handle, nat.ptr(z), n, int(t), nat.ptr(out), self._stream()))
+        return out.reshape(*lead, d, d)
+
+    def sample_g(self, p, subk, n_samples):
+        """Bernoulli graphs from edge probabilities p [d, d] (or [n, d, d] with subk [n, 2]) (dibs.py:102-119)."""
+        p = self._f32(p)
+        single = p.dim() == 2
+        p = p.reshape(-1, self.n_vars, self.n_vars)
+        n = p.shape[0]
+        keys = keys_to_device(np.asarray(as_key(subk)).reshape(n, 2), self.device)
+        out = torch.empty((n, n_samples, self.n_vars, self.n_vars), dtype=torch.int32, device=self.device)
+        plan = self._plan(n)
+        nat.check(nat.lib().dibs_sample_graphs(plan.handle, nat.ptr(p), nat.ptr(keys), n, int(n_samples), nat.ptr(out),
+                                               self._stream()))
+        return out[0] if single else out
+
+    def sample_soft_g(self, z, subk, n_samples, t):
+        """logistic noise (random.logistic) + particle_to_soft_graph (dibs.py:121-140,431): z [n,d,k,2] -> [n,S,d,d]."""
+        z = self._f32(z)
+        single = z.dim() == 3
+        z = z.reshape(-1, *z.shape[-3:])
+        n, d, k = z.shape[0], z.shape[1], z.shape[2]
+        keys = keys_to_device(np.asarray(as_key(subk)).reshape(n, 2), self.device)
+        out = torch.empty((n, n_samples, d, d), dtype=torch.float32, device=self.device)
+        plan = self._plan(n, k)
+        nat.check(nat.lib().dibs_soft_graphs(plan.handle, nat.ptr(z), nat.ptr(keys), n, int(n_samples), int(t), nat.ptr(out),
+                                             self._stream()))
+        return out[0] if single else out
+
+    # ------------------------------------------------------------------ likelihood estimators (dibs.py:255-551)
+    def eltwise_log_joint_prob(self, gs, single_theta, rng=None):
+        """log p(Theta, D | G) batched over graphs: gs [S, d, d] (+ single theta) or gs [n, S, d, d] (+ theta batch)."""
+        gs = self._f32(gs)
+        single = gs.dim() == 3
+        gs = gs.reshape(-1, *gs.shape[-3:]) if not single else gs[None]
+        n, s = gs.shape[0], gs.shape[1]
+        theta = None
+        if self.joint:
+            theta = single_theta
+            if single:
+                theta = _add_leading(theta)
+            theta = self._flat_theta(theta)
+        out = torch.empty((n, s), dtype=torch.float32, device=self.device)
+        plan = self._plan(n)
+        nat.check(nat.lib().dibs_log_joint_prob(plan.handle, nat.ptr(gs.contiguous()), nat.ptr(theta), n, s, nat.ptr(out),
+                                                self._stream()))
+        return out[0] if single else out
+
+    def eltwise_grad_z_likelihood(self, zs, thetas, baselines, t, subkeys):
+        """Batch of estimators of grad_Z log p(Theta, D | Z) (dibs.py:295-321) -> (grads [n,d,k,2], baselines [n])."""
+        if self.grad_estimator_z not in nat.ESTIMATOR:
+            raise ValueError(f'Unknown gradient estimator `{self.grad_estimator_z}`')
+        zs = self._f32(zs)
+        n, d, k = zs.shape[0], zs.shape[1], zs.shape[2]
+        theta = self._flat_theta(thetas) if self.joint else None
+        base = self._f32(baselines)
+        keys = keys_to_device(np.asarray(as_key(subkeys)).reshape(n, 2), self.device)
+        grad = torch.empty_like(zs)
+        base_out = torch.empty_like(base)
+        plan = self._plan(n, k)
+        nat.check(nat.lib().dibs_grad_z_likelihood(plan.handle, nat.ptr(zs), nat.ptr(theta), nat.ptr(base), int(t),
+                                                   nat.ptr(keys), n, nat.ptr(grad), nat.ptr(base_out), self._stream()))
+        return grad, base_out
+
+    def eltwise_grad_theta_likelihood(self, zs, thetas, t, subkeys):
+        """Batch of estimators of grad_Theta log p(Theta, D | Z) (dibs.py:467-551) -> flat [n, Dtheta]."""
+        zs = self._f32(zs)
+        n, k = zs.shape[0], zs.shape[2]
+        theta = self._flat_theta(thetas)
+        keys = keys_to_device(np.asarray(as_key(subkeys)).reshape(n, 2), self.device)
+        grad = torch.empty_like(theta)
+        plan = self._plan(n, k)
+        nat.check(nat.lib().dibs_grad_theta_likelihood(plan.handle, nat.ptr(zs), nat.ptr(theta), int(t), nat.ptr(keys), n,
+                                                       nat.ptr(grad), self._stream()))
+        return grad
+
+    # ------------------------------------------------------------------ latent prior (dibs.py:557-658)
+    def eltwise_grad_latent_prior(self, zs, subkeys, t, constraint_only=False):
+        """grad_Z log p(Z) = -beta(t) grad E[h(G)] - Z / sigma^2 + grad log p(G_alpha(Z)) (dibs.py:626-658)."""
+        zs = self._f32(zs)
+        n, k = zs.shape[0], zs.shape[2]
+        keys = keys_to_device(np.asarray(as_key(subkeys)).reshape(n, 2), self.device)
+        grad = torch.empty_like(zs)
+        plan = self._plan(n, k)
+        nat.check(nat.lib().dibs_grad_latent_prior(plan.handle, nat.ptr(zs), int(t), nat.ptr(keys), n, int(constraint_only),
+                                                   nat.ptr(grad), self._stream()))
+        return grad
+
+    def grad_constraint_gumbel(self, single_z, key, t):
+        """mean over Gumbel-soft graphs of grad_Z h(G) for one particle (dibs.py:576-601)."""
+        return self.eltwise_grad_latent_prior(self._f32(single_z)[None], np.asarray(as_key(key))[None], t,
+                                              constraint_only=True)[0]
+
+    def acyclic_constr(self, g):
+        """h(G) = tr((I + G/d)^d) - d, batched (dibs/graph_utils.py:8-30)."""
+        g = self._f32(g)
+        single = g.dim() == 2
+        g = g.reshape(-1, self.n_vars, self.n_vars)
+        out = torch.empty((g.shape[0],), dtype=torch.float32, device=self.device)
+        plan = self._plan(g.shape[0])
+        nat.check(nat.lib().dibs_acyclic_constr(plan.handle, nat.ptr(g), g.shape[0], nat.ptr(out), self._stream()))
+        return out[0] if single else out
+
+    def visualize_callback(self, ipython=True, save_path=None):
+        """Text-only progress callback (the reference plots with matplotlib, dibs.py:661-692: out of scope)."""
+        def callback(**kwargs):
+            zs = kwargs["zs"]
+            gs = self.particle_to_g_lim(zs)
+            n_cyclic = int((self.acyclic_constr(gs.to(torch.float32)) > 0).sum().item())
+            print(f'iteration {kwargs["t"]:6d} | alpha {self.alpha(kwargs["t"]):6.1f} | beta {self.beta(kwargs["t"]):6.1f} '
+                  f'| #cyclic {n_cyclic:3d}')
+        return callback
+
+
+def _add_leading(theta):
+    if theta is None:
+        return None
+    if isinstance(theta, torch.Tensor):
+        return theta[None]
+    if isinstance(theta, np.ndarray):
+        return theta[None]
+    return type(theta)(_add_leading(t) for t in theta)
+
+
+class _Plan:
+    """Owns one native ``dibs_plan``."""
+
+    def __init__(self, handle, cfg, owner):
+        self.handle, self.cfg, self.owner = handle, cfg, owner
+        self.n_local = cfg.n_particles // cfg.world_size
+        self.row0 = cfg.rank * self.n_local
+        self.theta_dim = nat.lib().dibs_theta_dim(handle)
+
+    def attach_nccl(self):
+        import torch.distributed as dist
+        dev = self.owner.device
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.cfg.rank == 0:
+            buf = np.zeros(128, np.uint8)
+            nat.check(nat.lib().dibs_nccl_unique_id(nat.ptr(buf)))
+            ident = torch.from_numpy(buf)
+        on_gpu = dist.get_backend() == "nccl"
+        ident = ident.to(dev) if on_gpu else ident
+        dist.broadcast(ident, src=0)
+        buf = np.ascontiguousarray(ident.cpu().numpy())
+        with torch.cuda.device(dev):
+            nat.check(nat.lib().dibs_plan_attach_nccl(self.handle, nat.ptr(buf)))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                nat.lib().dibs_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

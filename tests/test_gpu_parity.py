@@ -1,0 +1,287 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden fixtures and the NumPy oracle.
+
+Golden fixtures come from the reference's own sources (see tests/test_oracle_golden.py).  Tolerances:
+1e-5 relative on values (edge probabilities, log-probs, kernel matrix, h(G)); sampled adjacency bit-exact
+given identical edge probabilities; MC gradient estimators get an absolute floor proportional to the largest
+entry because softmax weights over log-probs of magnitude 1e2..1e4 amplify fp32 rounding.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import STEP_CASES, SAMPLE_CASES, load, oracle_config, assert_close
+from oracle import dibs_oracle as orc
+from oracle import threefry as tf
+
+pytestmark = pytest.mark.gpu
+
+
+def build_model(g, sample_case=False, **over):
+    from dibs_b200.inference import JointDiBS, MarginalDiBS
+    from dibs_b200.models import (BGe, LinearGaussian, DenseNonlinearGaussian, ErdosReniDAGDistribution,
+                                  ScaleFreeDAGDistribution, UniformDAGDistributionRejection)
+    lik, prior = str(g["lik"]), str(g["prior"])
+    d = g["x"].shape[1]
+    gm = {"er": lambda: ErdosReniDAGDistribution(n_vars=d, n_edges_per_node=int(g["n_edges_per_node"])),
+          "sf": lambda: ScaleFreeDAGDistribution(n_vars=d),
+          "uniform": lambda: UniformDAGDistributionRejection(n_vars=d)}[prior]()
+    kw = dict(x=g["x"], graph_model=gm, n_grad_mc_samples=int(g["n_grad_mc_samples"]),
+              n_acyclicity_mc_samples=int(g["n_acyclicity_mc_samples"]))
+    if not sample_case:
+        kw.update(interv_mask=g["interv_mask"], alpha_linear=float(g["alpha_linear"]), beta_linear=float(g["beta_linear"]),
+                  tau=float(g["tau"]), grad_estimator_z=str(g["estimator"]),
+                  score_function_baseline=float(g["score_function_baseline"]), optimizer=str(g["optimizer"]),
+                  latent_prior_std=float(g["latent_prior_std"]))
+    kw.update(over)
+    if lik == "bge":
+        return MarginalDiBS(likelihood_model=BGe(n_vars=d), **kw)
+    if lik == "lingauss":
+        return JointDiBS(likelihood_model=LinearGaussian(n_vars=d), **kw)
+    return JointDiBS(likelihood_model=DenseNonlinearGaussian(n_vars=d, hidden_layers=(int(g["hidden"]),)), **kw)
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def _grad_tol(ref):
+    return 3e-4 * max(1.0, float(np.abs(ref).max()))
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_graph_model_hooks(name):
+    g = load(name)
+    model = build_model(g)
+    t = int(g["t"])
+    assert_close(npy(model.edge_probs(g["z"], t)), g["edge_probs"], 1e-5, 1e-7, "edge_probs")
+    assert (npy(model.particle_to_g_lim(g["z"])) == g["g_lim"]).all()
+    s = int(g["n_grad_mc_samples"])
+    # bit-exact adjacency given the reference's edge probabilities and keys
+    got = npy(model.sample_g(g["edge_probs"], g["mc_keys"], s))
+    assert (got == g["sample_g"]).all()
+    soft = npy(model.sample_soft_g(g["z"], g["mc_keys"], s, t))
+    assert_close(soft, g["soft_g"], 1e-5, 2e-7, "soft_g")
+    assert_close(npy(model.acyclic_constr(g["sample_g"][:, 0].astype(np.float32))), g["acyclic_h_hard"], 1e-5, 1e-5, "h hard")
+    assert_close(npy(model.acyclic_constr(g["soft_g"][:, 0])), g["acyclic_h_soft"], 1e-5, 1e-5, "h soft")
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_log_joint_prob(name):
+    g = load(name)
+    model = build_model(g)
+    theta = g.get("theta")
+    lp = npy(model.eltwise_log_joint_prob(g["sample_g"].astype(np.float32), theta))
+    assert_close(lp, g["logprob_hard"], 1e-5, 1e-5, "logprob_hard")
+    if "logprob_soft" in g:
+        lp = npy(model.eltwise_log_joint_prob(g["soft_g"], theta))
+        assert_close(lp, g["logprob_soft"], 1e-5, 1e-5, "logprob_soft")
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_gradient_estimators(name):
+    g = load(name)
+    model = build_model(g)
+    t = int(g["t"])
+    theta = g.get("theta")
+    gz, nb = model.eltwise_grad_z_likelihood(g["z"], theta, g["sf_baseline"], t, g["mc_keys"])
+    ref = g["grad_z_likelihood"]
+    assert_close(npy(gz), ref, 3e-4, _grad_tol(ref), "grad_z_likelihood")
+    assert_close(npy(nb), g["sf_baseline_new"], 1e-5, 1e-6, "sf_baseline")
+    if theta is not None:
+        gt = model.eltwise_grad_theta_likelihood(g["z"], theta, t, g["mc_keys"])
+        ref = g["grad_theta_likelihood"]
+        assert_close(npy(gt), ref, 3e-4, _grad_tol(ref), "grad_theta_likelihood")
+    gc = model.eltwise_grad_latent_prior(g["z"], g["mc_keys"], t, constraint_only=True)
+    assert_close(npy(gc), g["grad_constraint"], 1e-4, 1e-5, "grad_constraint")
+    cfg = oracle_config(g)
+    if not (cfg.prior.kind == "er" and cfg.prior.p >= 1.0):
+        gp = model.eltwise_grad_latent_prior(g["z"], g["mc_keys"], t)
+        assert_close(npy(gp), g["grad_latent_prior"], 1e-4, 1e-4, "grad_latent_prior")
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_kernel_and_phi(name):
+    g = load(name)
+    model = build_model(g)
+    theta = g.get("theta")
+    k = npy(model._f_kernel_mat(g["z"], theta))
+    assert_close(k, g["kxx"], 1e-5, 1e-7, "kxx")
+    assert (k == k.T).all(), "kernel matrix must be bitwise symmetric"
+    if theta is None:
+        phi_z = model._parallel_update(g["z"], None, g["phi_in_grad_z"], None)[0]
+        assert_close(npy(phi_z), g["phi_z"], 1e-5, 1e-5, "phi_z")
+    else:
+        phi_z, phi_t = model._parallel_update(g["z"], theta, g["phi_in_grad_z"], g["phi_in_grad_theta"])
+        assert_close(npy(phi_z), g["phi_z"], 1e-5, 1e-5, "phi_z")
+        assert_close(npy(phi_t), g["phi_theta"], 1e-5, 1e-5, "phi_theta")
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_full_steps(name):
+    g = load(name)
+    cfg = oracle_config(g)
+    if cfg.prior.kind == "er" and cfg.prior.p >= 1.0:
+        pytest.skip("ER prior degenerate (p>=1) -> NaN in the reference too (SURVEY Q10)")
+    model = build_model(g)
+    t = int(g["t"])
+    z0 = g["z"]
+    th0 = g.get("theta")
+    zeros_t = None if th0 is None else np.zeros_like(th0)
+    for steps in (1, 2):
+        z, th, vz, vth, key, sf = model._svgd_loop(t, steps, (z0, th0, np.zeros_like(z0), zeros_t, g["key"], g["sf_baseline"]))
+        assert (key == g[f"step{steps}_key"]).all()
+        assert_close(npy(z), g[f"step{steps}_z"], 1e-5, 2e-5, f"z after {steps} step(s)")
+        assert_close(npy(sf), g[f"step{steps}_sf_baseline"], 1e-5, 1e-6, "sf_baseline")
+        if th0 is not None:
+            assert_close(npy(th), g[f"step{steps}_theta"], 1e-5, 2e-5, f"theta after {steps} step(s)")
+        if cfg.optimizer == "rmsprop":
+            ref = g[f"step{steps}_v_z"]
+            assert_close(npy(vz), ref, 1e-3, 1e-3 * float(ref.max()), "v_z")
+
+
+@pytest.mark.parametrize("name", SAMPLE_CASES)
+def test_sample_trajectories(name):
+    """sample() end to end vs the reference's trajectory: init parity, chunking + callbacks, final Z -> G."""
+    g = load(name)
+    model = build_model(g, sample_case=True)
+    steps, m, ce = int(g["steps"]), int(g["n_particles"]), int(g["callback_every"])
+    seen = {}
+
+    def cb(**kw):
+        seen[kw["t"]] = (npy(kw["zs"]), kw.get("thetas"))
+        assert kw["dibs"] is model
+
+    from dibs_b200.inference import PRNGKey
+    res = model.sample(key=PRNGKey(int(g["seed"])), n_particles=m, steps=steps, callback=cb, callback_every=ce)
+    n_run = -(-steps // ce) * ce
+    assert sorted(seen) == list(range(ce, n_run + 1, ce))          # Q2: ceil(steps/ce)*ce steps are run
+    assert_close(seen[ce][0], g[f"cb_t{ce}_z"], 1e-4, 2e-4, "z at first callback")
+    if f"cb_t{ce}_theta" in g:
+        th = model._flat_theta(seen[ce][1])
+        assert_close(npy(th), g[f"cb_t{ce}_theta"], 1e-4, 2e-4, "theta at first callback")
+    g_final = res[0] if isinstance(res, tuple) else res
+    assert g_final.dtype == torch.int32 and tuple(g_final.shape) == g["g_final"].shape
+    assert (npy(g_final) == g["g_final"]).mean() >= 0.9
+
+
+@pytest.mark.parametrize("lik", ["lingauss", "densenn", "bge"])
+def test_init_particles_vs_oracle(lik):
+    from dibs_b200.inference import PRNGKey
+    d, m = 7, 5
+    g = dict(load("step_joint_lingauss_er"))
+    rng = np.random.default_rng(0)
+    g["x"] = rng.normal(size=(30, d)).astype(np.float32)
+    g["lik"], g["prior"], g["hidden"] = np.array(lik), np.array("sf"), np.int32(3)
+    model = build_model(g, sample_case=True)
+    cfg = oracle_config(g, sample_case=True)
+    key = PRNGKey(42)
+    st = orc.init_particles(cfg, key, m, None, np.float32)
+    ks = tf.split(key, 2)
+    init = model._sample_initial_random_particles(key=ks[1], n_particles=m)
+    z, th = init if isinstance(init, tuple) else (init, None)
+    assert_close(npy(z), st.z, 2e-6, 2e-7, "init z")
+    if th is not None:
+        assert_close(npy(th), st.theta, 2e-6, 2e-7, "init theta")
+
+
+def _mid_case(lik, d=20, m=8, s=32, a=8, n_obs=100, hidden=5, seed=0):
+    from dibs_b200.synthetic import make_linear_gaussian_data, make_nonlinear_gaussian_data
+    data = (make_nonlinear_gaussian_data(seed=seed, n_vars=d, n_observations=n_obs, hidden=hidden) if lik == "densenn"
+            else make_linear_gaussian_data(seed=seed, n_vars=d, n_observations=n_obs))
+    g = dict(x=data["x"], lik=np.array(lik), prior=np.array("er"), n_edges_per_node=np.int32(2), hidden=np.int32(hidden),
+             n_grad_mc_samples=np.int32(s), n_acyclicity_mc_samples=np.int32(a))
+    return g
+
+
+@pytest.mark.parametrize("lik", ["lingauss", "densenn", "bge"])
+def test_step_vs_oracle_n_vars_20(lik):
+    """BASELINE-shaped problem (n_vars=20, N=100) at a particle count the oracle finishes in seconds:
+    values vs the fp32 oracle at 1e-5, estimators bounded by the fp32-vs-fp64 oracle gap."""
+    from dibs_b200.inference import PRNGKey
+    g = _mid_case(lik)
+    model = build_model(g, sample_case=True)
+    cfg = oracle_config(g, sample_case=True)
+    m, d = 8, 20
+    key = PRNGKey(3)
+    st32 = orc.init_particles(cfg, key, m, None, np.float32)
+    st32.z = (st32.z * 2.0).astype(np.float32)
+    t = 40
+    x, mask = g["x"], np.zeros(g["x"].shape, np.int32)
+    keys = tf.split(tf.prng_key(9), m)
+    alpha = orc.alpha_of(cfg, t, np.float32)
+    assert_close(npy(model.edge_probs(st32.z, t)), orc.edge_probs(st32.z, alpha), 1e-5, 1e-7, "edge_probs")
+    k_full, _, _ = orc.kernel_matrix(cfg, st32.z, st32.theta if cfg.joint else None, np.float32)
+    assert_close(npy(model._f_kernel_mat(st32.z, st32.theta)), k_full, 1e-5, 1e-7, "kernel matrix")
+    # log-probs of the graphs the reference would sample
+    p = orc.edge_probs(st32.z, alpha)
+    gs = np.stack([orc.sample_g(p[i], keys[i], cfg.n_grad_mc_samples) for i in range(m)])
+    assert (npy(model.sample_g(p, keys, cfg.n_grad_mc_samples)) == gs).all()
+    pre = orc.bge_precompute(x, mask, cfg.lik, np.float64) if lik == "bge" else None
+    lp64 = np.stack([orc.log_joint(cfg, gs[i], None if st32.theta is None else orc.theta_for_model(cfg, st32.theta[i].astype(np.float64)),
+                                   x, mask, np.float64, want_grads=False, pre=pre)[0] for i in range(m)])
+    lp = npy(model.eltwise_log_joint_prob(gs.astype(np.float32), st32.theta))
+    assert_close(lp, lp64, 1e-5, 1e-4, "log joint prob vs fp64 oracle")
+    # estimators: |cuda - o64| <= 4 |o32 - o64| + floor
+    for which in ("z", "theta", "prior"):
+        if which == "theta" and not cfg.joint:
+            continue
+        outs = {}
+        for dt in (np.float32, np.float64):
+            pre = orc.bge_precompute(x, mask, cfg.lik, dt) if lik == "bge" else None
+            rows = []
+            for i in range(m):
+                th = None if st32.theta is None else orc.theta_for_model(cfg, st32.theta[i].astype(dt))
+                zi = st32.z[i].astype(dt)
+                if which == "z":
+                    f = orc.grad_z_score_function if cfg.grad_estimator_z == "score" else orc.grad_z_reparam
+                    args = (cfg, zi, th, 0.0, t, keys[i], x, mask, dt) + ((pre,) if cfg.grad_estimator_z == "score" else ())
+                    rows.append(f(*args)[0])
+                elif which == "theta":
+                    rows.append(orc.grad_theta(cfg, zi, th, t, keys[i], x, mask, dt)[0].reshape(-1))
+                else:
+                    rows.append(orc.grad_latent_prior(cfg, zi, keys[i], t, st32.latent_prior_std, dt))
+            outs[dt] = np.stack(rows)
+        if which == "z":
+            got = npy(model.eltwise_grad_z_likelihood(st32.z, st32.theta, np.zeros(m, np.float32), t, keys)[0])
+        elif which == "theta":
+            got = npy(model.eltwise_grad_theta_likelihood(st32.z, st32.theta, t, keys))
+        else:
+            got = npy(model.eltwise_grad_latent_prior(st32.z, keys, t))
+        o32, o64 = outs[np.float32], outs[np.float64]
+        gap = np.abs(o32.astype(np.float64) - o64).max()
+        scale = np.abs(o64).max()
+        err = np.abs(got.astype(np.float64) - o64).max()
+        assert err <= 4 * gap + 2e-5 * scale + 1e-6, (which, err, gap, scale)
+
+
+def test_properties_full_size():
+    """Size-independent properties at BASELINE configs[1] shapes (n_vars=20, n_particles=256, n_mc=64)."""
+    from dibs_b200.inference import PRNGKey
+    g = _mid_case("lingauss", m=256, s=64, a=32)
+    model = build_model(g, sample_case=True)
+    m, d = 256, 20
+    init = model._sample_initial_random_particles(key=PRNGKey(1), n_particles=m)
+    z, th = init
+    # t = 0: alpha = 0 -> every off-diagonal edge probability is exactly 0.5 (Q1)
+    p0 = npy(model.edge_probs(z, 0))
+    off = ~np.eye(d, dtype=bool)
+    assert (p0[:, off] == 0.5).all() and (p0[:, ~off] == 0).all()
+    k = npy(model._f_kernel_mat(z, th))
+    assert (k == k.T).all()
+    assert_close(np.diag(k), np.full(m, 2.0), 0, 1e-6, "K_ii = scale_z + scale_theta")
+    assert (k > 0).all() and (k <= 2.0 + 1e-6).all()
+    # h(G) == 0 for DAGs, > 0 with a cycle
+    from dibs_b200.synthetic import sample_er_dag
+    rng = np.random.default_rng(0)
+    dags = np.stack([sample_er_dag(rng, d) for _ in range(16)]).astype(np.float32)
+    h = npy(model.acyclic_constr(dags))
+    assert np.abs(h).max() < 1e-4
+    cyc = dags.copy(); cyc[:, 0, 1] = 1; cyc[:, 1, 0] = 1
+    assert (npy(model.acyclic_constr(cyc)) > 1e-3).all()
+    # a full chunk of steps keeps everything finite and moves every particle
+    z1, th1, vz, vth, key, sf = model._svgd_loop(50, 3, (z, th, torch.zeros_like(z), torch.zeros_like(th), PRNGKey(5), np.zeros(m, np.float32)))
+    assert torch.isfinite(z1).all() and torch.isfinite(th1).all()
+    assert (z1 != z).any(dim=(1, 2, 3)).all()
+    # determinism: same inputs -> bitwise identical outputs
+    z2, th2, *_ = model._svgd_loop(50, 3, (z, th, torch.zeros_like(z), torch.zeros_like(th), PRNGKey(5), np.zeros(m, np.float32)))
+    assert torch.equal(z1, z2) and torch.equal(th1, th2)
