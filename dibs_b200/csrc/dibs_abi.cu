@@ -126,6 +126,7 @@ struct dibs_plan {
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
     int kernels_per_step = 0;
     bool use_graph = true;
+    cudaStream_t cap_stream = nullptr;
     // NCCL
     NcclComm comm = nullptr;
 };
@@ -243,6 +244,7 @@ extern "C" int dibs_plan_destroy(dibs_plan* p) {
     if (!p) return DIBS_OK;
     for (int i = 0; i < 2; ++i) if (p->gexec[i]) cudaGraphExecDestroy(p->gexec[i]);
     if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
+    if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
     void* ptrs[] = {p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->v, p->base, p->st,
                     p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->dist_part, p->kz, p->kt, p->kfull};
     for (void* q : ptrs) if (q) cudaFree(q);
@@ -511,9 +513,11 @@ extern "C" int dibs_svgd_steps(dibs_plan* p, int32_t t_start, int32_t n_steps, f
         for (int par = 0; par < 2; ++par) {
             long long before = g_launches.load();
             cudaGraph_t g = nullptr;
-            CU(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-            int r = enqueue_step(p, par, stream);
-            cudaError_t e = cudaStreamEndCapture(stream, &g);
+            // capture on a plan-owned stream (the caller's may be the legacy default stream, which cannot capture)
+            if (!p->cap_stream) CU(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+            CU(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
+            int r = enqueue_step(p, par, p->cap_stream);
+            cudaError_t e = cudaStreamEndCapture(p->cap_stream, &g);
             if (r != DIBS_OK) { if (g) cudaGraphDestroy(g); return r; }
             if (e != cudaSuccess) return fail(DIBS_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
             CU(cudaGraphInstantiate(&p->gexec[par], g, 0));

