@@ -40,6 +40,7 @@ PROTOTYPES = {
     "dibs_nccl_unique_id": (ctypes.c_int, [_P]),
     "dibs_plan_attach_nccl": (ctypes.c_int, [_P, _P]),
     "dibs_svgd_steps": (ctypes.c_int, [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "dibs_svgd_steps_timed": (ctypes.c_int, [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, ctypes.c_int64, _P, _P]),
     "dibs_init_particles": (ctypes.c_int, [_P, _P, _P, _P, _P]),
     "dibs_edge_probs": (ctypes.c_int, [_P, _P, _I, _I, _P, _P]),
     "dibs_particle_to_g_lim": (ctypes.c_int, [_P, _P, _I, _P, _P]),
@@ -55,6 +56,8 @@ PROTOTYPES = {
     "dibs_prng_split": (ctypes.c_int, [_P, _I, _I, _P]),
     "dibs_launch_count": (ctypes.c_int64, []),
 }
+
+PHASES = ("mc_theta", "mc_z", "acyclic", "assemble", "allgather", "pair_dist", "pair_kernel", "phi_update")
 
 _lib = None
 

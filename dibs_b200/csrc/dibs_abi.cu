@@ -129,7 +129,25 @@ struct dibs_plan {
     cudaStream_t cap_stream = nullptr;
     // NCCL
     NcclComm comm = nullptr;
+    // optional per-kernel event timing (dibs_svgd_steps_timed): events recorded after each launch of an eager step
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_phase;     // phase id of the work that ENDS at ev_pool[i]; -1 = start marker
+    size_t ev_used = 0;
 };
+
+// mark the end of one kernel (phase) on `stream` when the plan is in timing mode
+static void mark(dibs_plan* p, cudaStream_t stream, int phase) {
+    if (!p->timing) return;
+    if (p->ev_used == p->ev_pool.size()) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        p->ev_pool.push_back(e);
+        p->ev_phase.push_back(0);
+    }
+    p->ev_phase[p->ev_used] = phase;
+    cudaEventRecord(p->ev_pool[p->ev_used++], stream);
+}
 
 static int pick_dmax(int d) {
     const int opts[] = {8, 16, 20, 32, 64, 128};
@@ -243,6 +261,7 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
 extern "C" int dibs_plan_destroy(dibs_plan* p) {
     if (!p) return DIBS_OK;
     for (int i = 0; i < 2; ++i) if (p->gexec[i]) cudaGraphExecDestroy(p->gexec[i]);
+    for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
     if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
     if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
     void* ptrs[] = {p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->v, p->base, p->st,
@@ -412,6 +431,7 @@ static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_st
         q.n_chunks = p->th_chunks; q.s_per_chunk = p->th_spc; q.gpb = p->gpb_th;
         q.part_acc = th_acc; q.acc_size = p->th_acc_size; q.part_stats = th_stats;
         TRY(launch_mc<MC_THETA_HARD>(p, q, stream));
+        mark(p, stream, DIBS_PHASE_MC_THETA);
     }
     fill_mc(p, s, q);
     q.which_split = joint ? 1 : 0; q.pre_split = 1;
@@ -419,7 +439,9 @@ static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_st
     q.part_acc = z_acc; q.acc_size = p->d * p->d; q.part_stats = z_stats;
     if (p->cfg.grad_estimator_z == DIBS_ESTIMATOR_SCORE) TRY(launch_mc<MC_Z_SCORE>(p, q, stream));
     else TRY(launch_mc<MC_Z_REPARAM>(p, q, stream));
+    mark(p, stream, DIBS_PHASE_MC_Z);
     TRY(launch_acyc(p, s, joint ? 2 : 1, acyc, stream));
+    mark(p, stream, DIBS_PHASE_ACYCLIC);
     AsmParams a;
     fill_asm(p, s, a);
     a.zacc = z_acc; a.zstats = z_stats; a.z_chunks = p->z_chunks;
@@ -428,6 +450,7 @@ static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_st
     a.acyc = acyc;
     a.grad_z = grad_z; a.gz_ld = gz_ld; a.grad_th = grad_th; a.gth_ld = gth_ld;
     TRY(launch_asm(p, a, stream));
+    mark(p, stream, DIBS_PHASE_ASSEMBLE);
     return DIBS_OK;
 }
 
@@ -442,18 +465,21 @@ static void fill_pair(const dibs_plan* p, PairParams& q) {
     q.n_step_splits = p->cfg.joint ? 3 : 2;
 }
 
-static int launch_pair(const PairParams& q, bool with_phi, cudaStream_t stream) {
+static int launch_pair(dibs_plan* p, const PairParams& q, bool with_phi, cudaStream_t stream) {
     dim3 g1(ceil_div(q.n_all, KT), ceil_div(q.n_rows, KT), q.n_split);
     k_pair_dist<<<g1, 256, 0, stream>>>(q);
     LAUNCHED();
+    mark(p, stream, DIBS_PHASE_PAIR_DIST);
     size_t plane = (size_t)q.n_rows * q.n_all;
     int blocks = (int)((plane + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
     k_pair_finish<<<blocks, 256, 0, stream>>>(q);
     LAUNCHED();
+    mark(p, stream, DIBS_PHASE_PAIR_KERNEL);
     if (with_phi) {
         dim3 g3(ceil_div(q.dz, PT_C) + ceil_div(q.dth, PT_C), ceil_div(q.n_rows, PT_I));
         k_phi_update<<<g3, 64, 0, stream>>>(q);
         LAUNCHED();
+        mark(p, stream, DIBS_PHASE_PHI_UPDATE);
     }
     return DIBS_OK;
 }
@@ -470,6 +496,7 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream) {
         if (!p->comm) return fail(DIBS_ERR_STATE, "world_size > 1 but no NCCL communicator attached");
         // the one exchange of the step: every rank contributes its rows [Z | Theta | dZ | dTheta] (in place)
         NC(g_nccl.AllGather(loc, P, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm, stream));
+        mark(p, stream, DIBS_PHASE_ALLGATHER);
     }
     PairParams q;
     fill_pair(p, q);
@@ -477,7 +504,7 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream) {
     q.x_next = Pn + (size_t)p->row0 * p->ld; q.next_ld = p->ld;
     q.v = p->v; q.v_ld = p->D;
     q.st = p->st;
-    TRY(launch_pair(q, true, stream));
+    TRY(launch_pair(p, q, true, stream));
     return DIBS_OK;
 }
 
@@ -486,8 +513,9 @@ __global__ void k_set_state(StepState* st, const uint32_t* key, int t) {
 }
 __global__ void k_get_key(const StepState* st, uint32_t* key) { key[0] = st->key[0]; key[1] = st->key[1]; }
 
-extern "C" int dibs_svgd_steps(dibs_plan* p, int32_t t_start, int32_t n_steps, float* z, float* theta, float* v_z,
-                               float* v_theta, uint32_t* key, float* sf_baseline, void* stream_) {
+static int svgd_steps_impl(dibs_plan* p, int32_t t_start, int32_t n_steps, float* z, float* theta, float* v_z,
+                           float* v_theta, uint32_t* key, float* sf_baseline, void* stream_, bool timed, int per_kernel,
+                           void* flush_buf, size_t flush_bytes, float* step_ms, float* phase_ms) {
     if (!p || !z || !key || !sf_baseline) return fail(DIBS_ERR_INVALID_ARG, "dibs_svgd_steps: null argument");
     if (!p->has_data) return fail(DIBS_ERR_STATE, "dibs_set_data has not been called");
     if (p->Dth && !theta) return fail(DIBS_ERR_INVALID_ARG, "theta is required for joint inference");
@@ -508,7 +536,8 @@ extern "C" int dibs_svgd_steps(dibs_plan* p, int32_t t_start, int32_t n_steps, f
     k_set_state<<<1, 1, 0, stream>>>(p->st, key, t_start);
     LAUNCHED();
 
-    const bool graph = p->use_graph && p->cfg.world_size == 1;
+    const bool graph = p->use_graph && p->cfg.world_size == 1 && !(timed && per_kernel);
+    p->ev_used = 0;
     if (graph && !p->gexec[0]) {
         for (int par = 0; par < 2; ++par) {
             long long before = g_launches.load();
@@ -528,11 +557,33 @@ extern "C" int dibs_svgd_steps(dibs_plan* p, int32_t t_start, int32_t n_steps, f
     }
     for (int i = 0; i < n_steps; ++i) {
         int cur = i & 1;
+        if (timed) {
+            // cold-L2 protocol: overwrite a buffer larger than L2 (untimed), then bracket the step with events
+            if (flush_buf) CU(cudaMemsetAsync(flush_buf, i & 0xff, flush_bytes, stream));
+            p->timing = true;
+            mark(p, stream, -1);
+            p->timing = per_kernel != 0;
+        }
         if (graph) {
             CU(cudaGraphLaunch(p->gexec[cur], stream));
             g_launches.fetch_add(p->kernels_per_step, std::memory_order_relaxed);
         } else {
             TRY(enqueue_step(p, cur, stream));
+        }
+        if (timed && !per_kernel) { p->timing = true; mark(p, stream, DIBS_N_PHASES); }
+        p->timing = false;
+    }
+    if (timed) {
+        // device time between consecutive events on the launching stream; a -1 marker starts a step
+        if (phase_ms) for (int i = 0; i < DIBS_N_PHASES; ++i) phase_ms[i] = 0.0f;
+        CU(cudaStreamSynchronize(stream));
+        int step = -1;
+        for (size_t i = 0; i < p->ev_used; ++i) {
+            if (p->ev_phase[i] < 0) { ++step; if (step_ms && step < n_steps) step_ms[step] = 0.0f; continue; }
+            float ms = 0.0f;
+            CU(cudaEventElapsedTime(&ms, p->ev_pool[i - 1], p->ev_pool[i]));
+            if (phase_ms && p->ev_phase[i] < DIBS_N_PHASES) phase_ms[p->ev_phase[i]] += ms;
+            if (step_ms && step >= 0 && step < n_steps) step_ms[step] += ms;
         }
     }
     float* locf = p->pk[n_steps & 1] + (size_t)p->row0 * p->ld;
@@ -546,6 +597,23 @@ extern "C" int dibs_svgd_steps(dibs_plan* p, int32_t t_start, int32_t n_steps, f
     k_get_key<<<1, 1, 0, stream>>>(p->st, key);
     LAUNCHED();
     return DIBS_OK;
+}
+
+extern "C" int dibs_svgd_steps(dibs_plan* p, int32_t t_start, int32_t n_steps, float* z, float* theta, float* v_z,
+                               float* v_theta, uint32_t* key, float* sf_baseline, void* stream) {
+    return svgd_steps_impl(p, t_start, n_steps, z, theta, v_z, v_theta, key, sf_baseline, stream, false, 0, nullptr, 0,
+                           nullptr, nullptr);
+}
+
+extern "C" int dibs_svgd_steps_timed(dibs_plan* p, int32_t t_start, int32_t n_steps, float* z, float* theta, float* v_z,
+                                     float* v_theta, uint32_t* key, float* sf_baseline, void* stream,
+                                     int32_t per_kernel, void* l2_flush_buf, int64_t l2_flush_bytes,
+                                     float* step_ms_host, float* phase_ms_host) {
+    if (!step_ms_host && !phase_ms_host) return fail(DIBS_ERR_INVALID_ARG, "dibs_svgd_steps_timed: no output buffer");
+    if (phase_ms_host && !per_kernel) return fail(DIBS_ERR_INVALID_ARG, "phase_ms_host needs per_kernel = 1");
+    if (l2_flush_buf && l2_flush_bytes <= 0) return fail(DIBS_ERR_INVALID_ARG, "l2_flush_bytes must be positive");
+    return svgd_steps_impl(p, t_start, n_steps, z, theta, v_z, v_theta, key, sf_baseline, stream, true, per_kernel,
+                           l2_flush_buf, (size_t)(l2_flush_buf ? l2_flush_bytes : 0), step_ms_host, phase_ms_host);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -766,7 +834,7 @@ static int hook_pair(dibs_plan* p, const float* z, const float* theta, const flo
     q.n_split = ns; q.split_len = sl; q.dist_part = dist; q.kz = kz; q.kt = p->Dth ? kt : nullptr; q.kfull = kf;
     q.x_all = xs; q.ld = D; q.g_all = gs; q.g_ld = D;
     if (phi_z) { TRY(sc.get(&phi, (size_t)n * D)); q.phi_out = phi; q.phi_ld = D; }
-    TRY(launch_pair(q, phi_z != nullptr, stream));
+    TRY(launch_pair(p, q, phi_z != nullptr, stream));
     if (phi_z) {
         CU(cudaMemcpy2DAsync(phi_z, fz, phi, fd, fz, n, cudaMemcpyDeviceToDevice, stream));
         if (phi_th && p->Dth) CU(cudaMemcpy2DAsync(phi_th, ft, phi + p->Dz, fd, ft, n, cudaMemcpyDeviceToDevice, stream));

@@ -110,6 +110,29 @@ int dibs_plan_attach_nccl(dibs_plan* plan, const uint8_t* id128_host);
 int dibs_svgd_steps(dibs_plan* plan, int32_t t_start, int32_t n_steps, float* z, float* theta,
                     float* v_z, float* v_theta, uint32_t* key, float* sf_baseline, void* stream);
 
+/* Measurement variant of the same loop for bench.py (the reference has no counterpart: its only timing is a
+ * `%%time` notebook cell, examples/dibs_marginal.ipynb:88).  Each step is bracketed by CUDA events on `stream`;
+ * if l2_flush_buf is non-NULL it is overwritten (cudaMemsetAsync of l2_flush_bytes > L2 size) before every step,
+ * outside the bracket, so every step starts with a cold L2.  per_kernel = 0: steps run exactly like
+ * dibs_svgd_steps (CUDA-graph replay), step_ms_host[n_steps] receives each step's device time.
+ * per_kernel = 1: steps are launched eagerly with an event after every kernel; phase_ms_host[DIBS_N_PHASES]
+ * receives the summed device time of each kernel over the n_steps.  Synchronises `stream`. */
+enum {
+    DIBS_PHASE_MC_THETA = 0,    /* grad_theta estimator pass  (dibs.py:488-551)              */
+    DIBS_PHASE_MC_Z = 1,        /* grad_z likelihood pass     (dibs.py:325-459)              */
+    DIBS_PHASE_ACYCLIC = 2,     /* grad_constraint_gumbel     (dibs.py:576-601)              */
+    DIBS_PHASE_ASSEMBLE = 3,    /* chain rule + latent prior  (dibs.py:626-658)              */
+    DIBS_PHASE_ALLGATHER = 4,   /* NCCL all-gather (multi-GPU only)                          */
+    DIBS_PHASE_PAIR_DIST = 5,   /* pairwise squared distances (kernel.py:30,66-71)           */
+    DIBS_PHASE_PAIR_KERNEL = 6, /* exp -> K                   (kernel.py:30,66-71)           */
+    DIBS_PHASE_PHI_UPDATE = 7,  /* phi + optimizer            (svgd.py:194-224,591-670,265)  */
+    DIBS_N_PHASES = 8
+};
+int dibs_svgd_steps_timed(dibs_plan* plan, int32_t t_start, int32_t n_steps, float* z, float* theta,
+                          float* v_z, float* v_theta, uint32_t* key, float* sf_baseline, void* stream,
+                          int32_t per_kernel, void* l2_flush_buf, int64_t l2_flush_bytes,
+                          float* step_ms_host, float* phase_ms_host);
+
 /* replaces: _sample_initial_random_particles (svgd.py:125-148, 489-515) incl.
  * likelihood_model.sample_parameters (linearGaussian.py:212-227, nonlinearGaussian.py:155-186).
  * `key` is the sub-key handed to that function; fills the full [M, ...] arrays (every rank
