@@ -13,10 +13,12 @@
 
 #include "common.cuh"
 #include "kernels_mc.cuh"
+#include "kernels_mc_lin_qr.cuh"
 #include "kernels_mc_bge.cuh"
 #include "bge_prepare.cuh"
 #include "kernels_mc_nn.cuh"
 #include "kernels_prior.cuh"
+#include "kernels_acyclic.cuh"
 #include "kernels_pair.cuh"
 #include "kernels_init.cuh"
 
@@ -116,8 +118,11 @@ struct dibs_plan {
     float* v = nullptr;            // [M_loc][D]
     float* base = nullptr;         // [M_loc]
     StepState* st = nullptr;
+    // LinearGaussian, observational data, d <= 32: packed upper-triangular QR factor of x (kernels_mc_lin_qr.cuh)
+    bool use_qr = false;
+    std::vector<float> lin_r;
     // MC workspace
-    int gpb_th = 1, gpb_z = 1, th_chunks = 1, z_chunks = 1, th_spc = 1, z_spc = 1, th_acc_size = 0;
+    int max_chunks = 1, th_acc_size = 0;
     float *th_acc = nullptr, *th_stats = nullptr, *z_acc = nullptr, *z_stats = nullptr, *acyc = nullptr;
     // pairwise workspace
     int n_split = 1, split_len = 0;
@@ -159,14 +164,50 @@ static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 extern "C" int dibs_theta_dim(const dibs_plan* plan) { return plan ? plan->Dth : 0; }
 
-static void choose_chunks(int S, int gpb, int n_local, int* chunks, int* spc) {
+// How one Monte-Carlo pass over `n_local` particles x S samples is cut into CTAs.
+struct McShape {
+    bool qr;        // QR-form LinearGaussian kernel: the units below are sample PAIRS (slots)
+    int gpb;        // graphs (or slots) per block-round
+    int chunks;     // CTAs per particle (blockIdx.y)
+    int spc;        // samples (or slots) per chunk
+    int threads;    // CTA size
+};
+
+static bool qr_eligible(int likelihood, int dmax) { return likelihood == DIBS_LIK_LINEAR_GAUSSIAN && dmax <= 32; }
+
+static McShape mc_shape_for(bool qr, int likelihood, int d, int hidden, int n_local, int S) {
+    McShape sh;
+    sh.qr = qr;
+    if (n_local < 1) n_local = 1;
+    if (qr) {
+        const int Q = (S + 1) / 2;
+        int best = 1; long best_cost = -1;
+        for (int g = 1; g * d <= 192 && g <= Q; ++g) {
+            long cost = (long)ceil_div(Q, g) * (((g * d) + 31) / 32 * 32);
+            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = g; }
+        }
+        sh.gpb = best;
+        sh.threads = ((best * d) + 31) / 32 * 32;
+        const int rounds = ceil_div(Q, best);
+        int chunks = ceil_div(8 * 148, n_local);
+        if (chunks > rounds) chunks = rounds;
+        if (chunks < 1) chunks = 1;
+        const int rpc = ceil_div(rounds, chunks);
+        sh.chunks = ceil_div(rounds, rpc);
+        sh.spc = rpc * best;
+        return sh;
+    }
+    int per_item = (likelihood == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN) ? d * nn_hp(hidden) : d;
+    int gpb = 256 / per_item; if (gpb < 1) gpb = 1; if (gpb > S) gpb = S;
+    sh.gpb = gpb;
+    sh.threads = 256;
     int max_chunks = ceil_div(S, gpb);
-    int want = ceil_div(2 * 148, n_local > 0 ? n_local : 1);
+    int want = ceil_div(2 * 148, n_local);
     if (want < 1) want = 1;
     if (want > max_chunks) want = max_chunks;
-    int per = ceil_div(ceil_div(S, want), gpb) * gpb;
-    *spc = per;
-    *chunks = ceil_div(S, per);
+    sh.spc = ceil_div(ceil_div(S, want), gpb) * gpb;
+    sh.chunks = ceil_div(S, sh.spc);
+    return sh;
 }
 
 extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
@@ -214,11 +255,15 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
     if (const char* e = getenv("DIBS_B200_NO_GRAPH")) p->use_graph = !(e[0] == '1');
 
     const int d = p->d, S = c.n_grad_mc_samples;
-    int per_item = (c.likelihood == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN) ? d * nn_hp(c.hidden) : d;
-    int gpb = 256 / per_item; if (gpb < 1) gpb = 1; if (gpb > S) gpb = S;
-    p->gpb_th = p->gpb_z = gpb;
-    choose_chunks(S, gpb, p->M_loc, &p->th_chunks, &p->th_spc);
-    p->z_chunks = p->th_chunks; p->z_spc = p->th_spc;
+    {
+        // workspace for the larger of the two possible pass shapes (the QR path is chosen in dibs_set_data)
+        McShape a = mc_shape_for(false, c.likelihood, d, c.hidden, p->M_loc, S);
+        p->max_chunks = a.chunks;
+        if (qr_eligible(c.likelihood, p->dmax)) {
+            McShape b = mc_shape_for(true, c.likelihood, d, c.hidden, p->M_loc, S);
+            if (b.chunks > p->max_chunks) p->max_chunks = b.chunks;
+        }
+    }
     p->th_acc_size = p->Dth;
 
     auto alloc = [&](void** ptr, size_t bytes) -> int {
@@ -232,10 +277,10 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
         (r = alloc((void**)&p->v, (size_t)p->M_loc * p->D * sizeof(float))) ||
         (r = alloc((void**)&p->base, (size_t)p->M_loc * sizeof(float))) ||
         (r = alloc((void**)&p->st, sizeof(StepState))) ||
-        (r = alloc((void**)&p->z_acc, (size_t)p->M_loc * p->z_chunks * d * d * sizeof(float))) ||
-        (r = alloc((void**)&p->z_stats, (size_t)p->M_loc * p->z_chunks * 4 * sizeof(float))) ||
-        (r = alloc((void**)&p->th_acc, (size_t)p->M_loc * p->th_chunks * p->th_acc_size * sizeof(float))) ||
-        (r = alloc((void**)&p->th_stats, (size_t)p->M_loc * p->th_chunks * 4 * sizeof(float))) ||
+        (r = alloc((void**)&p->z_acc, (size_t)p->M_loc * p->max_chunks * d * d * sizeof(float))) ||
+        (r = alloc((void**)&p->z_stats, (size_t)p->M_loc * p->max_chunks * 4 * sizeof(float))) ||
+        (r = alloc((void**)&p->th_acc, (size_t)p->M_loc * p->max_chunks * p->th_acc_size * sizeof(float))) ||
+        (r = alloc((void**)&p->th_stats, (size_t)p->M_loc * p->max_chunks * 4 * sizeof(float))) ||
         (r = alloc((void**)&p->acyc, (size_t)p->M_loc * d * d * sizeof(float)))) {
         dibs_plan_destroy(p);
         return r;
@@ -271,6 +316,36 @@ extern "C" int dibs_plan_destroy(dibs_plan* p) {
     return DIBS_OK;
 }
 
+// Thin QR of x [n_obs, d] by Householder reflections in fp64; returns the upper-triangular factor (rows beyond
+// min(n_obs, d) are zero) packed like RTri<dmax> and rounded to fp32.  Only R^T R = x^T x matters downstream, so the
+// sign convention of the reflections is irrelevant.
+static void qr_upper_packed(const std::vector<float>& x, int n_obs, int d, int dmax, std::vector<float>& out) {
+    std::vector<double> a((size_t)n_obs * d);
+    for (size_t i = 0; i < a.size(); ++i) a[i] = (double)x[i];
+    const int r = n_obs < d ? n_obs : d;
+    std::vector<double> v(n_obs);
+    for (int c = 0; c < r; ++c) {
+        double norm = 0.0;
+        for (int i = c; i < n_obs; ++i) norm += a[(size_t)i * d + c] * a[(size_t)i * d + c];
+        norm = std::sqrt(norm);
+        if (norm == 0.0) continue;
+        const double a0 = a[(size_t)c * d + c];
+        const double alpha = a0 > 0.0 ? -norm : norm;
+        double vnorm2 = 0.0;
+        for (int i = c; i < n_obs; ++i) { v[i] = a[(size_t)i * d + c] - (i == c ? alpha : 0.0); vnorm2 += v[i] * v[i]; }
+        if (vnorm2 == 0.0) continue;
+        for (int k = c; k < d; ++k) {
+            double dot = 0.0;
+            for (int i = c; i < n_obs; ++i) dot += v[i] * a[(size_t)i * d + k];
+            const double f = 2.0 * dot / vnorm2;
+            for (int i = c; i < n_obs; ++i) a[(size_t)i * d + k] -= f * v[i];
+        }
+    }
+    out.assign((size_t)dmax * (dmax + 1) / 2, 0.0f);
+    for (int i = 0; i < r; ++i)
+        for (int k = i; k < d; ++k) out[(size_t)i * dmax - (size_t)i * (i - 1) / 2 + (k - i)] = (float)a[(size_t)i * d + k];
+}
+
 extern "C" int dibs_set_data(dibs_plan* p, const float* x, const int32_t* mask, int32_t n_obs,
                              const float* bge_mean_obs_host, void* stream_) {
     if (!p || !x || n_obs < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_set_data: bad arguments");
@@ -294,6 +369,14 @@ extern "C" int dibs_set_data(dibs_plan* p, const float* x, const int32_t* mask, 
             CU(cudaMemcpyAsync(p->mask, mask, h.size() * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
         }
     }
+    p->use_qr = false;
+    if (qr_eligible(p->cfg.likelihood, p->dmax) && !p->has_mask && !getenv("DIBS_B200_NO_QR")) {
+        std::vector<float> hx((size_t)n_obs * d);
+        CU(cudaMemcpyAsync(hx.data(), p->x, hx.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        qr_upper_packed(hx, n_obs, d, p->dmax, p->lin_r);
+        p->use_qr = true;
+    }
     if (p->cfg.likelihood == DIBS_LIK_BGE) TRY(bge_prepare(p->cfg, d, n_obs, p->x, p->mask, bge_mean_obs_host, &p->bge_r,
                                                        &p->bge_table, &p->bge_coef, &p->bge_r_stride, stream, g_last_error));
     p->has_data = true;
@@ -303,6 +386,14 @@ extern "C" int dibs_set_data(dibs_plan* p, const float* x, const int32_t* mask, 
 // ------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------
+// pass shape for this plan: the QR kernel needs observational data and -- unless the graphs are supplied by the
+// caller (lp_only hook) -- the legacy threefry layout with an even number of samples (two draws per block)
+static McShape mc_shape(const dibs_plan* p, int n_local, int S, bool lp_only) {
+    const bool qr = p->use_qr && (lp_only || (!p->cfg.prng_partitionable && (S % 2) == 0));
+    return mc_shape_for(qr, p->cfg.likelihood, p->d, p->cfg.hidden, n_local, S);
+}
+static void apply_shape(McParams& q, const McShape& sh) { q.n_chunks = sh.chunks; q.s_per_chunk = sh.spc; q.gpb = sh.gpb; }
+
 struct Src {                 // where the particles of a launch live
     const float* z; int z_ld;
     const float* theta; int th_ld;
@@ -341,14 +432,34 @@ DECL_MC(lingauss, 8) DECL_MC(lingauss, 16) DECL_MC(lingauss, 20) DECL_MC(lingaus
 DECL_MC(nn, 8) DECL_MC(nn, 16) DECL_MC(nn, 20) DECL_MC(nn, 32) DECL_MC(nn, 64) DECL_MC(nn, 128)
 DECL_MC(bge, 8) DECL_MC(bge, 16) DECL_MC(bge, 20) DECL_MC(bge, 32) DECL_MC(bge, 64)
 #undef DECL_MC
+namespace dibs {
+int launch_mc_linqr_8(int, const McParams&, dim3, int, size_t, const float*, cudaStream_t);
+int launch_mc_linqr_16(int, const McParams&, dim3, int, size_t, const float*, cudaStream_t);
+int launch_mc_linqr_20(int, const McParams&, dim3, int, size_t, const float*, cudaStream_t);
+int launch_mc_linqr_32(int, const McParams&, dim3, int, size_t, const float*, cudaStream_t);
+}
 
 // the register-tiled MC kernels are instantiated per DMAX in mc_*_inst.cu (parallel build)
 template <int MODE>
-static int launch_mc(const dibs_plan* p, McParams q, cudaStream_t stream) {
+static int launch_mc(const dibs_plan* p, McParams q, const McShape& sh, cudaStream_t stream) {
+    apply_shape(q, sh);
     dim3 grid(q.n_local, q.n_chunks);
     const int lik = p->cfg.likelihood;
     size_t smem = 0;
     int e = 0;
+    if (sh.qr) {
+        smem = mc_lin_qr_smem(p->d, p->k, q.gpb);
+        if (smem > 227 * 1024) return fail(DIBS_ERR_UNSUPPORTED, "problem size needs more than 227 KB of shared memory per CTA");
+        switch (p->dmax) {
+            case 8: e = launch_mc_linqr_8(MODE, q, grid, sh.threads, smem, p->lin_r.data(), stream); break;
+            case 16: e = launch_mc_linqr_16(MODE, q, grid, sh.threads, smem, p->lin_r.data(), stream); break;
+            case 20: e = launch_mc_linqr_20(MODE, q, grid, sh.threads, smem, p->lin_r.data(), stream); break;
+            default: e = launch_mc_linqr_32(MODE, q, grid, sh.threads, smem, p->lin_r.data(), stream); break;
+        }
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (e != 0) return fail(DIBS_ERR_CUDA, std::string("MC kernel launch: ") + cudaGetErrorString((cudaError_t)e));
+        return DIBS_OK;
+    }
     if (lik == DIBS_LIK_LINEAR_GAUSSIAN) {
         smem = mc_lingauss_smem(p->d, p->k, p->N, q.gpb, p->dmax, q.mask != nullptr);
     } else if (lik == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN) {
@@ -385,7 +496,18 @@ static int launch_acyc(const dibs_plan* p, const Src& s, int which_split, float*
     a.keys_override = s.keys; a.t_override = s.t;
     a.alpha_linear = p->cfg.alpha_linear; a.tau = p->cfg.tau; a.ds_out = ds_out;
     const int d = p->d;
-    if (d <= 32) {
+    if (d <= 32 && (a.n_samples % 2) == 0 && !a.partitionable && !getenv("DIBS_B200_OLD_ACYCLIC")) {
+        // row-per-lane kernel: a warp per sample pair (both lanes of each threefry block are used)
+        int warps = a.n_samples / 2 < 8 ? a.n_samples / 2 : 8;
+        size_t smem = acyclic_rows_smem(d, p->k, p->dmax, warps);
+        while (smem > 200 * 1024 && warps > 1) { warps /= 2; smem = acyclic_rows_smem(d, p->k, p->dmax, warps); }
+        switch (p->dmax) {
+            case 8: TRY(set_smem(k_acyclic_rows<8>, smem)); k_acyclic_rows<8><<<s.n, warps * 32, smem, stream>>>(a); break;
+            case 16: TRY(set_smem(k_acyclic_rows<16>, smem)); k_acyclic_rows<16><<<s.n, warps * 32, smem, stream>>>(a); break;
+            case 20: TRY(set_smem(k_acyclic_rows<20>, smem)); k_acyclic_rows<20><<<s.n, warps * 32, smem, stream>>>(a); break;
+            default: TRY(set_smem(k_acyclic_rows<32>, smem)); k_acyclic_rows<32><<<s.n, warps * 32, smem, stream>>>(a); break;
+        }
+    } else if (d <= 32) {
         int warps = a.n_samples < 8 ? a.n_samples : 8;
         size_t smem = acyclic_smem(d, p->k, warps);
         while (smem > 200 * 1024 && warps > 1) { warps /= 2; smem = acyclic_smem(d, p->k, warps); }
@@ -424,29 +546,28 @@ static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_st
                          float* acyc, const float* base_in, float* base_out, float* grad_z, int gz_ld, float* grad_th,
                          int gth_ld, cudaStream_t stream) {
     const bool joint = p->cfg.joint;
+    const McShape sh = mc_shape(p, s.n, p->cfg.n_grad_mc_samples, false);
     McParams q;
     if (joint) {
         fill_mc(p, s, q);
         q.which_split = 0; q.pre_split = 0;
-        q.n_chunks = p->th_chunks; q.s_per_chunk = p->th_spc; q.gpb = p->gpb_th;
         q.part_acc = th_acc; q.acc_size = p->th_acc_size; q.part_stats = th_stats;
-        TRY(launch_mc<MC_THETA_HARD>(p, q, stream));
+        TRY(launch_mc<MC_THETA_HARD>(p, q, sh, stream));
         mark(p, stream, DIBS_PHASE_MC_THETA);
     }
     fill_mc(p, s, q);
     q.which_split = joint ? 1 : 0; q.pre_split = 1;
-    q.n_chunks = p->z_chunks; q.s_per_chunk = p->z_spc; q.gpb = p->gpb_z;
     q.part_acc = z_acc; q.acc_size = p->d * p->d; q.part_stats = z_stats;
-    if (p->cfg.grad_estimator_z == DIBS_ESTIMATOR_SCORE) TRY(launch_mc<MC_Z_SCORE>(p, q, stream));
-    else TRY(launch_mc<MC_Z_REPARAM>(p, q, stream));
+    if (p->cfg.grad_estimator_z == DIBS_ESTIMATOR_SCORE) TRY(launch_mc<MC_Z_SCORE>(p, q, sh, stream));
+    else TRY(launch_mc<MC_Z_REPARAM>(p, q, sh, stream));
     mark(p, stream, DIBS_PHASE_MC_Z);
     TRY(launch_acyc(p, s, joint ? 2 : 1, acyc, stream));
     mark(p, stream, DIBS_PHASE_ACYCLIC);
     AsmParams a;
     fill_asm(p, s, a);
-    a.zacc = z_acc; a.zstats = z_stats; a.z_chunks = p->z_chunks;
+    a.zacc = z_acc; a.zstats = z_stats; a.z_chunks = sh.chunks;
     a.baselines_in = base_in; a.baselines_out = base_out;
-    if (joint) { a.thacc = th_acc; a.thstats = th_stats; a.th_chunks = p->th_chunks; a.th_dim = p->Dth; }
+    if (joint) { a.thacc = th_acc; a.thstats = th_stats; a.th_chunks = sh.chunks; a.th_dim = p->Dth; }
     a.acyc = acyc;
     a.grad_z = grad_z; a.gz_ld = gz_ld; a.grad_th = grad_th; a.gth_ld = gth_ld;
     TRY(launch_asm(p, a, stream));
@@ -733,8 +854,9 @@ extern "C" int dibs_log_joint_prob(dibs_plan* p, const float* g, const float* th
     McParams q;
     fill_mc(p, s, q);
     q.n_samples = n_samples; q.g_ext = g; q.lp_out = lp_out;
-    q.gpb = p->gpb_z < n_samples ? p->gpb_z : n_samples; q.n_chunks = 1; q.s_per_chunk = n_samples;
-    TRY(launch_mc<MC_LP_ONLY>(p, q, stream));
+    McShape sh = mc_shape(p, n, n_samples, true);
+    sh.chunks = 1; sh.spc = sh.qr ? (n_samples + 1) / 2 : n_samples;     // one CTA per particle, all samples
+    TRY(launch_mc<MC_LP_ONLY>(p, q, sh, stream));
     CU(cudaStreamSynchronize(stream));
     return DIBS_OK;
 }
@@ -745,21 +867,19 @@ static int hook_grads(dibs_plan* p, const float* z, const float* theta, const fl
     if (!p->has_data && what < 2) return fail(DIBS_ERR_STATE, "dibs_set_data has not been called");
     Scratch sc;
     Src s{z, p->Dz, theta, p->Dth, n, 0, nullptr, keys, t};
-    int chunks, spc;
-    const int gpb = p->gpb_z;
-    choose_chunks(p->cfg.n_grad_mc_samples, gpb, n, &chunks, &spc);
+    const McShape sh = mc_shape(p, n, p->cfg.n_grad_mc_samples, false);
+    const int chunks = sh.chunks;
     float *acc = nullptr, *stats = nullptr, *acyc = nullptr, *gz_tmp = nullptr;
     AsmParams a;
     fill_asm(p, s, a);
     McParams q;
     fill_mc(p, s, q);
-    q.n_chunks = chunks; q.s_per_chunk = spc; q.gpb = gpb;
     if (what == 0) {
         TRY(sc.get(&acc, (size_t)n * chunks * p->d * p->d));
         TRY(sc.get(&stats, (size_t)n * chunks * 4));
         q.pre_split = 1; q.part_acc = acc; q.acc_size = p->d * p->d; q.part_stats = stats;
-        if (p->cfg.grad_estimator_z == DIBS_ESTIMATOR_SCORE) TRY(launch_mc<MC_Z_SCORE>(p, q, stream));
-        else TRY(launch_mc<MC_Z_REPARAM>(p, q, stream));
+        if (p->cfg.grad_estimator_z == DIBS_ESTIMATOR_SCORE) TRY(launch_mc<MC_Z_SCORE>(p, q, sh, stream));
+        else TRY(launch_mc<MC_Z_REPARAM>(p, q, sh, stream));
         a.zacc = acc; a.zstats = stats; a.z_chunks = chunks; a.baselines_in = baselines; a.baselines_out = baselines_out;
         a.grad_z = grad_out; a.gz_ld = p->Dz;
     } else if (what == 1) {
@@ -768,7 +888,7 @@ static int hook_grads(dibs_plan* p, const float* z, const float* theta, const fl
         TRY(sc.get(&stats, (size_t)n * chunks * 4));
         TRY(sc.get(&gz_tmp, (size_t)n * p->Dz));
         q.pre_split = 0; q.part_acc = acc; q.acc_size = p->Dth; q.part_stats = stats;
-        TRY(launch_mc<MC_THETA_HARD>(p, q, stream));
+        TRY(launch_mc<MC_THETA_HARD>(p, q, sh, stream));
         a.thacc = acc; a.thstats = stats; a.th_chunks = chunks; a.th_dim = p->Dth;
         a.grad_z = gz_tmp; a.gz_ld = p->Dz; a.grad_th = grad_out; a.gth_ld = p->Dth;
     } else {

@@ -1,0 +1,255 @@
+// LinearGaussian Monte-Carlo pass, observational data, n_vars <= 32: QR-factor form.
+//
+// replaces (same reference functions as kernels_mc.cuh::k_mc_lingauss): dibs/models/linearGaussian.py:278-338
+// (log_prob_parameters, log_likelihood, interventional_log_joint_prob) under the estimators of
+// dibs/inference/dibs.py:325-459 (grad_z score / reparam) and :488-551 (grad_theta).
+//
+// The reference evaluates, per sampled graph, the N x d residual  R = x - x (G o Theta)  and needs from it only
+//   ssq_j = sum_n R_nj^2            (the Gaussian log-likelihood, linearGaussian.py:314-316)
+//   B_:j  = x^T R_:j                (every gradient).
+// With x = Q Rx (thin QR, done once per dibs_set_data in fp64) and u_j = e_j - (G o Theta)_:j:
+//   R_:j = x u_j = Q (Rx u_j)   =>   ssq_j = |Rx u_j|^2 ,   B_:j = Rx^T (Rx u_j).
+// Two d x d triangular mat-vecs per (graph, node) -- d^2 FMAs instead of 2 N d -- with the SAME conditioning
+// as the reference's direct form (a sum of squares of one fp32 mat-vec; no Gram-matrix cancellation).
+//
+// Work decomposition: CTA = (particle, chunk of sample PAIRS).  Per round the CTA first draws the entries of
+// gpb graph pairs into shared memory with a flat thread mapping, then thread = (pair q, node j) owns the
+// columns j of the two graphs s = q and s = q + S/2: in JAX's legacy threefry layout those two draws are the
+// two lanes of ONE threefry block (counter pair (e, e + n/2)), so no random bits are thrown away.  (Host side:
+// odd S or the partitionable PRNG layout fall back to k_mc_lingauss, which draws one entry per block.)
+// Rx lives in the kernel-parameter constant bank: with the mat-vec loops fully unrolled every FMA takes its
+// Rx operand from a uniform register (LDCU), no shared-memory traffic at all in the inner loops.
+#pragma once
+#include "common.cuh"
+#include "kernels_mc.cuh"
+
+namespace dibs {
+
+// packed upper triangle, row i / column k >= i at i*DMAX - i(i-1)/2 + (k - i); zero-padded to DMAX
+template <int DMAX>
+struct RTri { float v[DMAX * (DMAX + 1) / 2]; };
+
+template <int DMAX>
+__host__ __device__ constexpr int rtri_off(int i, int k) { return i * DMAX - i * (i - 1) / 2 + (k - i); }
+
+// uniform in [eps, 1) that random.logistic feeds to log(u) - log1p(-u)
+__device__ __forceinline__ float logistic_u_from_bits(uint32_t bits) {
+    const float eps = 1.1920928955078125e-07f;
+    return fmaxf(eps, __fadd_rn(__fmul_rn(bits_to_unit(bits), 1.0f - eps), eps));
+}
+
+// value of one graph entry from its random bits.  sa = P_ij (hard) | exp(-alpha s_ij) (soft, tau == 1) | alpha s_ij
+template <bool HARD>
+__device__ __forceinline__ float entry_from_bits(uint32_t bits, float sa, bool fast_soft, float tau) {
+    if (HARD) return bits_to_unit(bits) < sa ? 1.0f : 0.0f;
+    const float u = logistic_u_from_bits(bits);
+    // sigmoid(log(u/(1-u)) + a) = u / (u + (1-u) e^{-a}): the logistic noise and the sigmoid cancel analytically
+    if (fast_soft) return __fdividef(u, fmaf(1.0f - u, sa, u));
+    return sigmoidf_ref(tau * ((logf(u) - log1pf(-u)) + sa));
+}
+
+template <int DMAX, int MODE>
+__global__ void __launch_bounds__(192, (DMAX <= 20 ? 2 : 1)) k_mc_lin_qr(McParams p, RTri<DMAX> R) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr bool HARD = (MODE == MC_THETA_HARD || MODE == MC_Z_SCORE);
+    const int d = p.d, gpb = p.gpb;                    // gpb = sample pairs ("slots") per round
+    const int m = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+    const int t = p.st ? p.st->t : p.t_override;
+    const int S = p.n_samples, Qh = (S + 1) >> 1;      // slot q holds samples q and q + Qh
+
+    float* sA = smem;                       // [d*d]
+    float* sTh = sA + d * d;                // [d*d]
+    float* sLpTh = sTh + d * d;             // [d*d] logN(theta_ij; mean_edge, sig_edge)
+    float* sNode = sLpTh + d * d;           // [2*gpb*d]
+    float* sLpS = sNode + 2 * gpb * d;      // [2*gpb]
+    float* sBig = smem + ((3 * d * d + 2 * gpb * d + 2 * gpb + 3) & ~3);   // Z staging, later the running sums
+    float* sGall = sBig + max(gpb * d * d, 2 * d * p.k);                   // [gpb][2][d][d] graph entries of a round
+
+    const bool use_ext = p.g_ext != nullptr;
+    const bool fast_soft = !HARD && !use_ext && p.tau == 1.0f;
+    const float alpha = stage_scores(p, m, sBig, sA, HARD, t);
+    const float* throw_ = p.theta + (size_t)m * p.th_ld;
+    for (int e = tid; e < d * d; e += blockDim.x) {
+        const float th = throw_[e];
+        sTh[e] = th;
+        sLpTh[e] = norm_logpdf_pre(th, p.mean_edge, p.sig2_edge, p.lognorm_edge);
+        if (fast_soft) sA[e] = expf(-sA[e]);
+    }
+    const uint2 key = use_ext ? make_uint2(0, 0) : mc_key(p, m);
+    __syncthreads();
+
+    const int slot = tid / d, j = tid - slot * d;
+    const bool active = slot < gpb;
+    const int q_begin = c * p.s_per_chunk;
+    const int q_end = min(Qh, q_begin + p.s_per_chunk);
+    const float inv_s2 = 1.0f / p.s2, inv_se2 = 1.0f / p.sig2_edge;
+    const uint32_t n_total = (uint32_t)S * d * d;
+    const uint32_t half = n_total >> 1;
+
+    // softmax-weighted running sums live in shared memory (a private slot per thread): sAcc[slot][i*d+j]
+    float* sAcc = sBig + (size_t)slot * d * d + j;
+    if (active && MODE != MC_LP_ONLY) {
+#pragma unroll
+        for (int i = 0; i < DMAX; ++i)
+            if (i < d) sAcc[i * d] = 0.0f;
+    }
+    float m_run = -INFINITY, l_run = 0.0f, sum_lp = 0.0f;
+
+    for (int q0 = q_begin; q0 < q_end; q0 += gpb) {
+        // ---- phase 1: all threads draw the round's graph entries into shared memory (flat, coalesced)
+        const int dd = d * d;
+        for (int idx = tid; idx < gpb * dd; idx += blockDim.x) {
+            const int sl = idx / dd, ij = idx - sl * dd;
+            const int i = ij / d, jj = ij - i * d;
+            const int qq = q0 + sl;
+            float ga = 0.0f, gb = 0.0f;
+            if (qq < q_end && i != jj) {      // zero_diagonal (utils/func.py:117-125): diagonal draws are discarded
+                if (use_ext) {
+                    ga = p.g_ext[((size_t)m * S + qq) * dd + ij];
+                    if (qq + Qh < S) gb = p.g_ext[((size_t)m * S + qq + Qh) * dd + ij];
+                } else {
+                    // legacy threefry layout, S even: flat elements e0 and e0 + n/2 are the two lanes of one block
+                    const uint32_t e0 = (uint32_t)qq * dd + ij;
+                    const uint2 r = threefry2x32(key.x, key.y, e0, e0 + half);
+                    const float sa = sA[ij];
+                    ga = entry_from_bits<HARD>(r.x, sa, fast_soft, p.tau);
+                    gb = entry_from_bits<HARD>(r.y, sa, fast_soft, p.tau);
+                }
+            }
+            sGall[(size_t)(2 * sl) * dd + ij] = ga;
+            sGall[(size_t)(2 * sl + 1) * dd + ij] = gb;
+        }
+        __syncthreads();
+        // ---- phase 2: thread (slot, j) owns column j of the two graphs of its slot
+        const int q = q0 + slot;
+        const bool v0 = active && q < q_end;
+        const bool v1 = v0 && q + Qh < S;
+        const float* sG0 = sGall + (size_t)(2 * slot) * dd + j;     // sG0[i*d] = G_s0[i][j]
+        const float* sG1 = sG0 + dd;
+        float u0[DMAX], u1[DMAX];
+        float prior0 = 0.0f, prior1 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < DMAX; ++i) {
+            float ga = 0.0f, gb = 0.0f, th = 0.0f;
+            if (v0 && i < d) {
+                ga = sG0[i * d]; gb = sG1[i * d];
+                th = sTh[i * d + j];
+                // log p(theta | G): sum g * logN(theta; mean_edge, sig_edge)   (linearGaussian.py:289)
+                const float lpth = sLpTh[i * d + j];
+                prior0 = fmaf(ga, lpth, prior0);
+                prior1 = fmaf(gb, lpth, prior1);
+            }
+            // u = e_j - (G o Theta)_:j
+            u0[i] = (i == j) ? 1.0f : -ga * th;
+            u1[i] = (i == j) ? 1.0f : -gb * th;
+        }
+        // y = Rx u (in place, ascending rows), ssq = |y|^2
+        float ssq0 = 0.0f, ssq1 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < DMAX; ++i) {
+            float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+            for (int k = i; k < DMAX; ++k) {
+                const float r = R.v[rtri_off<DMAX>(i, k)];
+                a0 = fmaf(r, u0[k], a0);
+                a1 = fmaf(r, u1[k], a1);
+            }
+            u0[i] = a0; u1[i] = a1;
+            ssq0 = fmaf(a0, a0, ssq0);
+            ssq1 = fmaf(a1, a1, ssq1);
+        }
+        // b = Rx^T y (in place, descending columns) = column j of x^T (x - x (G o Theta))
+#pragma unroll
+        for (int k = DMAX - 1; k >= 0; --k) {
+            float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+            for (int i = 0; i <= k; ++i) {
+                const float r = R.v[rtri_off<DMAX>(i, k)];
+                a0 = fmaf(r, u0[i], a0);
+                a1 = fmaf(r, u1[i], a1);
+            }
+            u0[k] = a0; u1[k] = a1;
+        }
+        if (v0) {
+            const float cst = (float)p.n_obs * p.log2pis2;
+            sNode[(2 * slot) * d + j] = prior0 - 0.5f * (cst + ssq0 * inv_s2);
+            sNode[(2 * slot + 1) * d + j] = prior1 - 0.5f * (cst + ssq1 * inv_s2);
+        }
+        __syncthreads();
+        if (tid < 2 * gpb) {
+            const int sl = tid >> 1, wh = tid & 1;
+            const int s = q0 + sl + wh * Qh;
+            float lp = -INFINITY;
+            if (q0 + sl < q_end && s < S) {
+                lp = 0.0f;
+                for (int jj = 0; jj < d; ++jj) lp += sNode[tid * d + jj];
+                if (p.lp_out) p.lp_out[(size_t)m * S + s] = lp;
+            }
+            sLpS[tid] = lp;
+        }
+        __syncthreads();
+        if (MODE != MC_LP_ONLY) {
+            float m_new = m_run;
+            for (int g = 0; g < 2 * gpb; ++g) m_new = fmaxf(m_new, sLpS[g]);
+            const float scale = (m_run == -INFINITY) ? 0.0f : expf(m_run - m_new);
+            float lsum = 0.0f, lpsum = 0.0f;
+            for (int g = 0; g < 2 * gpb; ++g) {
+                const float lp = sLpS[g];
+                if (lp != -INFINITY) { lsum += expf(lp - m_new); lpsum += lp; }
+            }
+            l_run = l_run * scale + lsum;
+            sum_lp += lpsum;
+            m_run = m_new;
+            const float e0 = v0 ? expf(sLpS[2 * slot] - m_new) : 0.0f;
+            const float e1 = v1 ? expf(sLpS[2 * slot + 1] - m_new) : 0.0f;
+#pragma unroll
+            for (int i = 0; i < DMAX; ++i) {
+                float val0 = 0.0f, val1 = 0.0f;
+                if (v0 && i < d) {
+                    const float ga = sG0[i * d], gb = sG1[i * d];
+                    if (MODE == MC_THETA_HARD) {
+                        // d/dtheta: g * (-(theta-mu)/sig^2) + g * (x^T R)/s2          
+                        const float th = sTh[i * d + j];
+                        const float pr = -(th - p.mean_edge) * inv_se2;
+                        val0 = ga * (pr + u0[i] * inv_s2);
+                        val1 = gb * (pr + u1[i] * inv_s2);
+                    } else if (MODE == MC_Z_REPARAM) {
+                        // dS = d lp/dG * tau*alpha*g(1-g)                                (App. B-4, B-6)
+                        const float th = sTh[i * d + j];
+                        const float lpth = sLpTh[i * d + j];
+                        val0 = (lpth + th * u0[i] * inv_s2) * (p.tau * alpha) * ga * (1.0f - ga);
+                        val1 = (lpth + th * u1[i] * inv_s2) * (p.tau * alpha) * gb * (1.0f - gb);
+                    } else {
+                        val0 = ga; val1 = gb;   // score function: weighted mean graph (App. B-2)
+                    }
+                }
+                if (v0 && i < d) sAcc[i * d] = sAcc[i * d] * scale + (e0 * val0 + e1 * val1);
+            }
+        }
+        __syncthreads();
+    }
+    if (MODE == MC_LP_ONLY) return;
+
+    // deterministic reduction over the slots: sRed[slot][i*d+j]
+    float* sRed = sBig;
+    float* out = p.part_acc + ((size_t)m * p.n_chunks + c) * p.acc_size;
+    for (int e = tid; e < d * d; e += blockDim.x) {
+        float sum = 0.0f;
+        for (int g = 0; g < gpb; ++g) sum += sRed[(size_t)g * d * d + e];
+        out[e] = sum;
+    }
+    if (tid == 0) {
+        float* stv = p.part_stats + ((size_t)m * p.n_chunks + c) * 4;
+        stv[0] = m_run; stv[1] = l_run; stv[2] = sum_lp; stv[3] = 0.0f;
+    }
+}
+
+inline size_t mc_lin_qr_smem(int d, int k, int gpb) {
+    size_t head = (3 * (size_t)d * d + 2 * (size_t)gpb * d + 2 * gpb + 3) & ~(size_t)3;
+    size_t big = (size_t)gpb * d * d;
+    if ((size_t)2 * d * k > big) big = (size_t)2 * d * k;
+    big += (size_t)2 * gpb * d * d;
+    return (head + big + 4) * sizeof(float);
+}
+
+}  // namespace dibs
