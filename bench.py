@@ -107,6 +107,7 @@ def kernel_work(name, m_loc, m_all):
     w["allgather"] = dict(flops=0, bytes=(m_all - m_loc) * 4 * 2 * dd, bound="nvlink")
     w["pair_dist"] = dict(flops=3 * m_loc * m_all * dd, bytes=4 * (m_all * dd + m_loc * m_all), bound="fp32")
     w["pair_kernel"] = dict(flops=4 * m_loc * m_all, bytes=4 * m_loc * m_all * (3 if dth else 2), bound="hbm")
+    w["step_keys"] = dict(flops=0, bytes=m_loc * 8 * (3 if lik != "bge" else 2), bound="latency")
     w["phi_update"] = dict(flops=2 * 2 * m_loc * m_all * dd, bytes=4 * (2 * m_all * dd + 4 * m_loc * dd + 2 * m_loc * m_all),
                            bound="fp32")
     return w

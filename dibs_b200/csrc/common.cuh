@@ -38,6 +38,32 @@ __host__ __device__ __forceinline__ uint2 threefry2x32(uint32_t k0, uint32_t k1,
     return make_uint2(x0, x1);
 }
 
+// N independent blocks in lock step: the 20-round chain of one block is strictly serial (3 dependent ALU ops per
+// round), so kernels that draw many entries per thread interleave N chains to fill the 4-cycle ALU latency.
+template <int N>
+__device__ __forceinline__ void threefry2x32_n(uint32_t k0, uint32_t k1, uint32_t (&x0)[N], uint32_t (&x1)[N]) {
+    const uint32_t k2 = k0 ^ k1 ^ 0x1BD11BDAu;
+#define DIBS_TFN_ROUND(r)                                             \
+    _Pragma("unroll") for (int q = 0; q < N; ++q) {                   \
+        x0[q] += x1[q]; x1[q] = rotl32(x1[q], r); x1[q] ^= x0[q];    \
+    }
+#define DIBS_TFN_INJECT(a, b, c)                                      \
+    _Pragma("unroll") for (int q = 0; q < N; ++q) { x0[q] += (a); x1[q] += (b) + (c); }
+    DIBS_TFN_INJECT(k0, k1, 0u)
+    DIBS_TFN_ROUND(13) DIBS_TFN_ROUND(15) DIBS_TFN_ROUND(26) DIBS_TFN_ROUND(6)
+    DIBS_TFN_INJECT(k1, k2, 1u)
+    DIBS_TFN_ROUND(17) DIBS_TFN_ROUND(29) DIBS_TFN_ROUND(16) DIBS_TFN_ROUND(24)
+    DIBS_TFN_INJECT(k2, k0, 2u)
+    DIBS_TFN_ROUND(13) DIBS_TFN_ROUND(15) DIBS_TFN_ROUND(26) DIBS_TFN_ROUND(6)
+    DIBS_TFN_INJECT(k0, k1, 3u)
+    DIBS_TFN_ROUND(17) DIBS_TFN_ROUND(29) DIBS_TFN_ROUND(16) DIBS_TFN_ROUND(24)
+    DIBS_TFN_INJECT(k1, k2, 4u)
+    DIBS_TFN_ROUND(13) DIBS_TFN_ROUND(15) DIBS_TFN_ROUND(26) DIBS_TFN_ROUND(6)
+    DIBS_TFN_INJECT(k2, k0, 5u)
+#undef DIBS_TFN_ROUND
+#undef DIBS_TFN_INJECT
+}
+
 // random_bits(key, shape)[e] for a flat array of n 32-bit draws.
 // legacy layout (jax_threefry_partitionable=False): counters arange(n) padded to even length,
 // first half -> lane 0, second half -> lane 1 (jax._src.prng.threefry_2x32).
@@ -145,6 +171,7 @@ __device__ __forceinline__ uint2 step_particle_key(const StepState* st, int whic
     if (next) *next = jax_split_row(key, 0u, n_particles + 1u, partitionable);
     return jax_split_row(key, m + 1u, n_particles + 1u, partitionable);
 }
+
 #endif
 
 }  // namespace dibs

@@ -118,6 +118,8 @@ struct dibs_plan {
     float* v = nullptr;            // [M_loc][D]
     float* base = nullptr;         // [M_loc]
     StepState* st = nullptr;
+    uint32_t* step_keys = nullptr;  // [n_splits][M_loc][2] sub-keys of the current step (k_prologue)
+    float* scores = nullptr;        // [M_loc][d*d] raw U V^T of the current step (k_prologue)
     // LinearGaussian, observational data, d <= 32: packed upper-triangular QR factor of x (kernels_mc_lin_qr.cuh)
     bool use_qr = false;
     std::vector<float> lin_r;
@@ -125,7 +127,7 @@ struct dibs_plan {
     int max_chunks = 1, th_acc_size = 0;
     float *th_acc = nullptr, *th_stats = nullptr, *z_acc = nullptr, *z_stats = nullptr, *acyc = nullptr;
     // pairwise workspace
-    int n_split = 1, split_len = 0;
+    int n_split = 1, n_split_z = 1, split_len_z = 0, split_len_t = 0;
     float *dist_part = nullptr, *kz = nullptr, *kt = nullptr, *kfull = nullptr;
     // CUDA graphs of one step, per buffer parity
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
@@ -277,6 +279,8 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
         (r = alloc((void**)&p->v, (size_t)p->M_loc * p->D * sizeof(float))) ||
         (r = alloc((void**)&p->base, (size_t)p->M_loc * sizeof(float))) ||
         (r = alloc((void**)&p->st, sizeof(StepState))) ||
+        (r = alloc((void**)&p->step_keys, (size_t)3 * p->M_loc * 2 * sizeof(uint32_t))) ||
+        (r = alloc((void**)&p->scores, (size_t)p->M_loc * p->d * p->d * sizeof(float))) ||
         (r = alloc((void**)&p->z_acc, (size_t)p->M_loc * p->max_chunks * d * d * sizeof(float))) ||
         (r = alloc((void**)&p->z_stats, (size_t)p->M_loc * p->max_chunks * 4 * sizeof(float))) ||
         (r = alloc((void**)&p->th_acc, (size_t)p->M_loc * p->max_chunks * p->th_acc_size * sizeof(float))) ||
@@ -285,16 +289,22 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
         dibs_plan_destroy(p);
         return r;
     }
-    // pairwise: split the feature axis until the distance pass has >= ~148 CTAs
-    int tiles = ceil_div(p->M, KT) * ceil_div(p->M_loc, KT);
-    int ns = ceil_div(148, tiles);
-    int max_ns = ceil_div(p->D, 2 * KF);
-    if (ns > max_ns) ns = max_ns;
-    if (ns < 1) ns = 1;
-    p->split_len = ceil_div(ceil_div(p->D, ns), KF) * KF;
-    p->n_split = ceil_div(p->D, p->split_len);
+    // pairwise: split the feature axis until the distance pass has >= ~2 x 148 CTAs; Z and Theta features are cut
+    // separately so that a split never straddles the Z | Theta boundary
+    {
+        int tiles = ceil_div(p->M, KT) * ceil_div(p->M_loc, KT);
+        int ns = ceil_div(2 * 148, tiles);
+        int max_ns = ceil_div(p->D, 2 * KF);
+        if (ns > max_ns) ns = max_ns;
+        if (ns < 1) ns = 1;
+        int len = ceil_div(ceil_div(p->D, ns), KF) * KF;
+        p->split_len_z = len < p->Dz ? len : ceil_div(p->Dz, KF) * KF;
+        p->n_split_z = ceil_div(p->Dz, p->split_len_z);
+        p->split_len_t = p->Dth ? (len < p->Dth ? len : ceil_div(p->Dth, KF) * KF) : KF;
+        p->n_split = p->n_split_z + (p->Dth ? ceil_div(p->Dth, p->split_len_t) : 0);
+    }
     size_t plane = (size_t)p->M_loc * p->M * sizeof(float);
-    if ((r = alloc((void**)&p->dist_part, plane * 2 * p->n_split)) || (r = alloc((void**)&p->kz, plane)) ||
+    if ((r = alloc((void**)&p->dist_part, plane * p->n_split)) || (r = alloc((void**)&p->kz, plane)) ||
         (r = alloc((void**)&p->kt, plane)) || (r = alloc((void**)&p->kfull, plane))) {
         dibs_plan_destroy(p);
         return r;
@@ -309,7 +319,7 @@ extern "C" int dibs_plan_destroy(dibs_plan* p) {
     for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
     if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
     if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
-    void* ptrs[] = {p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->v, p->base, p->st,
+    void* ptrs[] = {p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->v, p->base, p->st, p->step_keys, p->scores,
                     p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->dist_part, p->kz, p->kt, p->kfull};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
@@ -399,12 +409,18 @@ struct Src {                 // where the particles of a launch live
     const float* theta; int th_ld;
     int n; int m_offset;
     const StepState* st;
-    const uint32_t* keys; int t;
+    const uint32_t* keys; int t;         // per-particle sub-keys [n][2] (hooks) ...
+    const uint32_t* step_keys;           // ... or [n_splits][n][2] written by k_prologue (step loop)
+    const float* scores;                 // [n][d*d] raw U V^T written by k_prologue
 };
+
+static const uint32_t* pass_keys(const Src& s, int which) {
+    return s.step_keys ? s.step_keys + (size_t)which * s.n * 2 : s.keys;
+}
 
 static void fill_mc(const dibs_plan* p, const Src& s, McParams& q) {
     memset(&q, 0, sizeof(q));
-    q.z = s.z; q.z_ld = s.z_ld; q.theta = s.theta; q.th_ld = s.th_ld;
+    q.z = s.z; q.z_ld = s.z_ld; q.theta = s.theta; q.th_ld = s.th_ld; q.scores = s.scores;
     q.n_local = s.n; q.m_offset = s.m_offset; q.n_particles = p->M;
     q.d = p->d; q.k = p->k; q.n_obs = p->N; q.n_samples = p->cfg.n_grad_mc_samples;
     q.x = p->x; q.mask = p->has_mask ? p->mask : nullptr;
@@ -448,7 +464,7 @@ static int launch_mc(const dibs_plan* p, McParams q, const McShape& sh, cudaStre
     size_t smem = 0;
     int e = 0;
     if (sh.qr) {
-        smem = mc_lin_qr_smem(p->d, p->k, q.gpb);
+        smem = mc_lin_qr_smem(p->dmax, q.gpb);
         if (smem > 227 * 1024) return fail(DIBS_ERR_UNSUPPORTED, "problem size needs more than 227 KB of shared memory per CTA");
         switch (p->dmax) {
             case 8: e = launch_mc_linqr_8(MODE, q, grid, sh.threads, smem, p->lin_r.data(), stream); break;
@@ -490,10 +506,10 @@ static int launch_mc(const dibs_plan* p, McParams q, const McShape& sh, cudaStre
 static int launch_acyc(const dibs_plan* p, const Src& s, int which_split, float* ds_out, cudaStream_t stream) {
     AcycParams a;
     memset(&a, 0, sizeof(a));
-    a.z = s.z; a.z_ld = s.z_ld; a.n_local = s.n; a.m_offset = s.m_offset; a.n_particles = p->M;
+    a.z = s.z; a.z_ld = s.z_ld; a.scores = s.scores; a.n_local = s.n; a.m_offset = s.m_offset; a.n_particles = p->M;
     a.d = p->d; a.k = p->k; a.n_samples = p->cfg.n_acyclicity_mc_samples;
     a.st = s.st; a.which_split = which_split; a.partitionable = p->cfg.prng_partitionable;
-    a.keys_override = s.keys; a.t_override = s.t;
+    a.keys_override = pass_keys(s, which_split); a.t_override = s.t;
     a.alpha_linear = p->cfg.alpha_linear; a.tau = p->cfg.tau; a.ds_out = ds_out;
     const int d = p->d;
     if (d <= 32 && (a.n_samples % 2) == 0 && !a.partitionable && !getenv("DIBS_B200_OLD_ACYCLIC")) {
@@ -524,7 +540,7 @@ static int launch_acyc(const dibs_plan* p, const Src& s, int which_split, float*
 
 static void fill_asm(const dibs_plan* p, const Src& s, AsmParams& a) {
     memset(&a, 0, sizeof(a));
-    a.z = s.z; a.z_ld = s.z_ld; a.n_local = s.n; a.d = p->d; a.k = p->k;
+    a.z = s.z; a.z_ld = s.z_ld; a.scores = s.scores; a.n_local = s.n; a.d = p->d; a.k = p->k;
     a.st = s.st; a.t_override = s.t;
     a.alpha_linear = p->cfg.alpha_linear; a.beta_linear = p->cfg.beta_linear;
     a.n_samples = p->cfg.n_grad_mc_samples; a.sf_coef = p->cfg.score_function_baseline;
@@ -541,6 +557,22 @@ static int launch_asm(const dibs_plan* p, const AsmParams& a, cudaStream_t strea
     return DIBS_OK;
 }
 
+// scores + per-pass sub-keys for `n` particles (see k_prologue)
+static int launch_prologue(dibs_plan* p, const float* z, int z_ld, int n, int m_offset, const StepState* st,
+                           const uint32_t* keys_in, int n_splits, uint32_t pre_split_mask, float* scores,
+                           uint32_t* keys_out, cudaStream_t stream) {
+    PrologueParams q;
+    memset(&q, 0, sizeof(q));
+    q.z = z; q.z_ld = z_ld; q.n_local = n; q.m_offset = m_offset; q.n_particles = p->M; q.d = p->d; q.k = p->k;
+    q.st = st; q.keys_in = keys_in; q.n_splits = n_splits; q.pre_split_mask = pre_split_mask;
+    q.partitionable = p->cfg.prng_partitionable; q.scores = scores; q.keys_out = keys_out;
+    size_t smem = (size_t)2 * p->d * p->k * sizeof(float);
+    TRY(set_smem(k_prologue, smem));
+    k_prologue<<<n, 128, smem, stream>>>(q);
+    LAUNCHED();
+    return DIBS_OK;
+}
+
 // gradient phase for `s.n` particles: MC passes -> acyclicity -> assemble
 static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_stats, float* z_acc, float* z_stats,
                          float* acyc, const float* base_in, float* base_out, float* grad_z, int gz_ld, float* grad_th,
@@ -550,13 +582,13 @@ static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_st
     McParams q;
     if (joint) {
         fill_mc(p, s, q);
-        q.which_split = 0; q.pre_split = 0;
+        q.which_split = 0; q.keys_override = pass_keys(s, 0);
         q.part_acc = th_acc; q.acc_size = p->th_acc_size; q.part_stats = th_stats;
         TRY(launch_mc<MC_THETA_HARD>(p, q, sh, stream));
         mark(p, stream, DIBS_PHASE_MC_THETA);
     }
     fill_mc(p, s, q);
-    q.which_split = joint ? 1 : 0; q.pre_split = 1;
+    q.which_split = joint ? 1 : 0; q.keys_override = pass_keys(s, q.which_split);
     q.part_acc = z_acc; q.acc_size = p->d * p->d; q.part_stats = z_stats;
     if (p->cfg.grad_estimator_z == DIBS_ESTIMATOR_SCORE) TRY(launch_mc<MC_Z_SCORE>(p, q, sh, stream));
     else TRY(launch_mc<MC_Z_REPARAM>(p, q, sh, stream));
@@ -578,7 +610,8 @@ static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_st
 static void fill_pair(const dibs_plan* p, PairParams& q) {
     memset(&q, 0, sizeof(q));
     q.n_all = p->M; q.row0 = p->row0; q.n_rows = p->M_loc; q.dz = p->Dz; q.dth = p->Dth;
-    q.n_split = p->n_split; q.split_len = p->split_len; q.dist_part = p->dist_part;
+    q.n_split = p->n_split; q.n_split_z = p->n_split_z; q.split_len_z = p->split_len_z; q.split_len_t = p->split_len_t;
+    q.dist_part = p->dist_part;
     q.kz = p->kz; q.kt = p->Dth ? p->kt : nullptr; q.kfull = p->kfull;
     q.h_z = p->cfg.h_latent; q.h_t = p->cfg.h_theta; q.scale_z = p->cfg.scale_latent; q.scale_t = p->cfg.scale_theta;
     q.optimizer = p->cfg.optimizer; q.stepsize = p->cfg.stepsize;
@@ -598,7 +631,7 @@ static int launch_pair(dibs_plan* p, const PairParams& q, bool with_phi, cudaStr
     mark(p, stream, DIBS_PHASE_PAIR_KERNEL);
     if (with_phi) {
         dim3 g3(ceil_div(q.dz, PT_C) + ceil_div(q.dth, PT_C), ceil_div(q.n_rows, PT_I));
-        k_phi_update<<<g3, 64, 0, stream>>>(q);
+        k_phi_update<<<g3, 128, 0, stream>>>(q);
         LAUNCHED();
         mark(p, stream, DIBS_PHASE_PHI_UPDATE);
     }
@@ -610,7 +643,13 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream) {
     float* P = p->pk[cur];
     float* Pn = p->pk[cur ^ 1];
     float* loc = P + (size_t)p->row0 * p->ld;
-    Src s{loc, p->ld, p->Dth ? loc + p->Dz : nullptr, p->ld, p->M_loc, p->row0, p->st, nullptr, 0};
+    // the z-likelihood estimators split their sub-key before drawing (dibs.py:350,430); theta-grad and the
+    // acyclicity constraint draw with the sub-key itself (dibs.py:510,595)
+    const int n_splits = p->cfg.joint ? 3 : 2;
+    TRY(launch_prologue(p, loc, p->ld, p->M_loc, p->row0, p->st, nullptr, n_splits, p->cfg.joint ? 2u : 1u, p->scores,
+                        p->step_keys, stream));
+    mark(p, stream, DIBS_PHASE_STEP_KEYS);
+    Src s{loc, p->ld, p->Dth ? loc + p->Dz : nullptr, p->ld, p->M_loc, p->row0, p->st, nullptr, 0, p->step_keys, p->scores};
     TRY(enqueue_grads(p, s, p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->base, p->base,
                       loc + p->D, p->ld, p->Dth ? loc + p->D + p->Dz : nullptr, p->ld, stream));
     if (p->cfg.world_size > 1) {
@@ -850,7 +889,7 @@ extern "C" int dibs_log_joint_prob(dibs_plan* p, const float* g, const float* th
     float* zdummy;
     TRY(sc.get(&zdummy, (size_t)n * p->Dz));
     CU(cudaMemsetAsync(zdummy, 0, (size_t)n * p->Dz * sizeof(float), stream));
-    Src s{zdummy, p->Dz, theta, p->Dth, n, 0, nullptr, nullptr, 0};
+    Src s{zdummy, p->Dz, theta, p->Dth, n, 0, nullptr, nullptr, 0, nullptr, nullptr};
     McParams q;
     fill_mc(p, s, q);
     q.n_samples = n_samples; q.g_ext = g; q.lp_out = lp_out;
@@ -866,7 +905,11 @@ static int hook_grads(dibs_plan* p, const float* z, const float* theta, const fl
                       float* grad_out, float* baselines_out, cudaStream_t stream) {
     if (!p->has_data && what < 2) return fail(DIBS_ERR_STATE, "dibs_set_data has not been called");
     Scratch sc;
-    Src s{z, p->Dz, theta, p->Dth, n, 0, nullptr, keys, t};
+    float* scores = nullptr; uint32_t* pkeys = nullptr;
+    TRY(sc.get(&scores, (size_t)n * p->d * p->d));
+    TRY(sc.get(&pkeys, (size_t)n * 2));
+    TRY(launch_prologue(p, z, p->Dz, n, 0, nullptr, keys, 1, what == 0 ? 1u : 0u, scores, pkeys, stream));
+    Src s{z, p->Dz, theta, p->Dth, n, 0, nullptr, pkeys, t, nullptr, scores};
     const McShape sh = mc_shape(p, n, p->cfg.n_grad_mc_samples, false);
     const int chunks = sh.chunks;
     float *acc = nullptr, *stats = nullptr, *acyc = nullptr, *gz_tmp = nullptr;
@@ -877,7 +920,7 @@ static int hook_grads(dibs_plan* p, const float* z, const float* theta, const fl
     if (what == 0) {
         TRY(sc.get(&acc, (size_t)n * chunks * p->d * p->d));
         TRY(sc.get(&stats, (size_t)n * chunks * 4));
-        q.pre_split = 1; q.part_acc = acc; q.acc_size = p->d * p->d; q.part_stats = stats;
+        q.part_acc = acc; q.acc_size = p->d * p->d; q.part_stats = stats;
         if (p->cfg.grad_estimator_z == DIBS_ESTIMATOR_SCORE) TRY(launch_mc<MC_Z_SCORE>(p, q, sh, stream));
         else TRY(launch_mc<MC_Z_REPARAM>(p, q, sh, stream));
         a.zacc = acc; a.zstats = stats; a.z_chunks = chunks; a.baselines_in = baselines; a.baselines_out = baselines_out;
@@ -887,7 +930,7 @@ static int hook_grads(dibs_plan* p, const float* z, const float* theta, const fl
         TRY(sc.get(&acc, (size_t)n * chunks * p->Dth));
         TRY(sc.get(&stats, (size_t)n * chunks * 4));
         TRY(sc.get(&gz_tmp, (size_t)n * p->Dz));
-        q.pre_split = 0; q.part_acc = acc; q.acc_size = p->Dth; q.part_stats = stats;
+        q.part_acc = acc; q.acc_size = p->Dth; q.part_stats = stats;
         TRY(launch_mc<MC_THETA_HARD>(p, q, sh, stream));
         a.thacc = acc; a.thstats = stats; a.th_chunks = chunks; a.th_dim = p->Dth;
         a.grad_z = gz_tmp; a.gz_ld = p->Dz; a.grad_th = grad_out; a.gth_ld = p->Dth;
@@ -946,12 +989,11 @@ static int hook_pair(dibs_plan* p, const float* z, const float* theta, const flo
     PairParams q;
     fill_pair(p, q);
     q.n_all = n; q.row0 = 0; q.n_rows = n;
-    int ns = p->n_split, sl = p->split_len;
     size_t plane = (size_t)n * n;
-    TRY(sc.get(&dist, plane * 2 * ns));
+    TRY(sc.get(&dist, plane * p->n_split));
     TRY(sc.get(&kz, plane)); TRY(sc.get(&kt, plane));
     if (!k_out) TRY(sc.get(&kf, plane)); else kf = k_out;
-    q.n_split = ns; q.split_len = sl; q.dist_part = dist; q.kz = kz; q.kt = p->Dth ? kt : nullptr; q.kfull = kf;
+    q.dist_part = dist; q.kz = kz; q.kt = p->Dth ? kt : nullptr; q.kfull = kf;
     q.x_all = xs; q.ld = D; q.g_all = gs; q.g_ld = D;
     if (phi_z) { TRY(sc.get(&phi, (size_t)n * D)); q.phi_out = phi; q.phi_ld = D; }
     TRY(launch_pair(p, q, phi_z != nullptr, stream));

@@ -58,19 +58,11 @@ __global__ void __launch_bounds__(256) k_acyclic_rows(AcycParams p) {
     float* sF = wbase + 2 * MAT;                        // [2][DMAX][DMAX]  tau alpha G (1 - G)
 
     const bool fast_soft = p.tau == 1.0f;
-    const float* zrow = p.z + (size_t)m * p.z_ld;
-    for (int e = tid; e < 2 * d * k; e += blockDim.x) sZ[e] = zrow[e];
-    __syncthreads();
     for (int e = tid; e < dd; e += blockDim.x) {
-        const int i = e / d, j = e - i * d;
-        float acc = 0.0f;
-        for (int kk = 0; kk < k; ++kk) acc = fmaf(sZ[(i * k + kk) * 2], sZ[(j * k + kk) * 2 + 1], acc);
-        const float a = alpha * acc;
+        const float a = alpha * p.scores[(size_t)m * dd + e];
         sS[e] = fast_soft ? expf(-a) : a;
     }
-    uint2 key;
-    if (p.keys_override) key = make_uint2(p.keys_override[2 * m], p.keys_override[2 * m + 1]);
-    else key = step_particle_key(p.st, p.which_split, (uint32_t)(p.m_offset + m), (uint32_t)p.n_particles, p.partitionable);
+    const uint2 key = make_uint2(p.keys_override[2 * m], p.keys_override[2 * m + 1]);
     // zero the padding of this warp's matrices once (rows / columns >= d are never written again)
     for (int e = lane; e < 4 * MAT; e += 32) wbase[e] = 0.0f;
     __syncthreads();
@@ -87,21 +79,32 @@ __global__ void __launch_bounds__(256) k_acyclic_rows(AcycParams p) {
 
     for (int a = warp; a < half_a; a += n_warps) {
         // ---- draw the two soft graphs (samples a and a + A/2) with all lanes
-        for (int e = lane; e < dd; e += 32) {
-            const int i = e / d, j = e - i * d;
-            float g0 = 0.0f, g1 = 0.0f;
-            if (i != j) {
-                const uint32_t e0 = (uint32_t)a * dd + e;
-                const uint2 r = threefry2x32(key.x, key.y, e0, e0 + half);
-                const float sa = sS[e];
-                g0 = entry_from_bits<false>(r.x, sa, fast_soft, p.tau);
-                g1 = entry_from_bits<false>(r.y, sa, fast_soft, p.tau);
+        constexpr int IL = 4;                 // independent threefry chains per lane
+        for (int eb = lane; eb < dd; eb += IL * 32) {
+            uint32_t x0[IL], x1[IL];
+#pragma unroll
+            for (int u = 0; u < IL; ++u) {
+                const uint32_t e0 = (uint32_t)a * dd + (eb + u * 32);
+                x0[u] = e0; x1[u] = e0 + half;
             }
-            const float eye = (i == j) ? 1.0f : 0.0f;
-            sM[i * DMAX + j] = eye + inv_d * g0;                     // graph_utils.py:22-25
-            sM[MAT + i * DMAX + j] = eye + inv_d * g1;
-            sF[i * DMAX + j] = ta * g0 * (1.0f - g0);
-            sF[MAT + i * DMAX + j] = ta * g1 * (1.0f - g1);
+            threefry2x32_n<IL>(key.x, key.y, x0, x1);
+#pragma unroll
+            for (int u = 0; u < IL; ++u) {
+                const int e = eb + u * 32;
+                if (e >= dd) continue;
+                const int i = __float2int_rz(((float)e + 0.5f) * inv_d), j = e - i * d;    // exact for e < 2^13
+                float g0 = 0.0f, g1 = 0.0f;
+                if (i != j) {
+                    const float sa = sS[e];
+                    g0 = entry_from_bits<false>(x0[u], sa, fast_soft, p.tau);
+                    g1 = entry_from_bits<false>(x1[u], sa, fast_soft, p.tau);
+                }
+                const float eye = (i == j) ? 1.0f : 0.0f;
+                sM[i * DMAX + j] = eye + inv_d * g0;                     // graph_utils.py:22-25
+                sM[MAT + i * DMAX + j] = eye + inv_d * g1;
+                sF[i * DMAX + j] = ta * g0 * (1.0f - g0);
+                sF[MAT + i * DMAX + j] = ta * g1 * (1.0f - g1);
+            }
         }
         __syncwarp();
 #pragma unroll 1

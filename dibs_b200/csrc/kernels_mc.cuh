@@ -18,6 +18,7 @@ enum { MC_THETA_HARD = 0, MC_Z_SCORE = 1, MC_Z_REPARAM = 2, MC_LP_ONLY = 3 };
 
 struct McParams {
     const float* z; int z_ld;            // particle latents, row stride (floats)
+    const float* scores;                 // [n_local][d*d] raw U V^T from k_prologue (null: caller supplies graphs)
     const float* theta; int th_ld;       // particle parameters (may be null)
     int n_local;                         // particles in this launch
     int m_offset;                        // global index of the first particle (key derivation)
@@ -27,9 +28,8 @@ struct McParams {
     const float* x;                      // [N, d]
     const int32_t* mask;                 // [N, d] or null
     const StepState* st; int which_split; int partitionable;
-    const uint32_t* keys_override;       // [n_local, 2] or null
+    const uint32_t* keys_override;       // [n_local, 2] per-particle sub-keys of this pass
     int t_override;                      // used when st == null
-    int pre_split;                       // 1: draw with split(key)[1] (dibs.py:350,430); 0: key itself (:510)
     float alpha_linear, tau;
     // LinearGaussian / DenseNN constants (fp32, rounded like the reference)
     float s2, log2pis2;                  // (sqrt(obs_noise))^2 and log(2 pi s2)
@@ -63,32 +63,24 @@ __device__ __forceinline__ float graph_entry(const McParams& p, uint2 key, const
     return sigmoidf_ref(tau * (logistic_from_bits(bits) + sA[i * d + j]));
 }
 
-// Shared prologue: scores alpha*U V^T (soft) or edge probabilities (hard) into sA; returns alpha.
-// sZ must hold 2*d*k floats of scratch.
-__device__ __forceinline__ float stage_scores(const McParams& p, int m, float* sZ, float* sA, bool hard, int t) {
-    const int d = p.d, k = p.k;
+// Shared prologue: alpha * scores (soft) or edge probabilities sigmoid(alpha * scores), zero diagonal (hard), into
+// sA[i*d + j]; returns alpha.  The raw scores U V^T come from k_prologue (one evaluation per particle per step).
+__device__ __forceinline__ float stage_scores(const McParams& p, int m, float* sA, bool hard, int t) {
+    const int d = p.d, dd = d * d;
     const float alpha = p.alpha_linear * (float)t;  // dibs.py:70: fp32 product of slope and step
-    const float* zrow = p.z + (size_t)m * p.z_ld;
-    for (int e = threadIdx.x; e < 2 * d * k; e += blockDim.x) sZ[e] = zrow[e];
-    __syncthreads();
-    for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
-        int i = e / d, j = e % d;
-        float acc = 0.0f;
-        for (int kk = 0; kk < k; ++kk) acc = fmaf(sZ[(i * k + kk) * 2], sZ[(j * k + kk) * 2 + 1], acc);
-        float a = alpha * acc;
-        sA[e] = hard ? (i == j ? 0.0f : sigmoidf_ref(a)) : a;
+    const float* srow = p.scores ? p.scores + (size_t)m * dd : nullptr;
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) {
+        const float a = srow ? alpha * srow[e] : 0.0f;
+        const int i = e / d;
+        sA[e] = hard ? (e == i * (d + 1) ? 0.0f : sigmoidf_ref(a)) : a;
     }
     __syncthreads();
     return alpha;
 }
 
+// per-particle key of this pass (already pre-split by k_prologue where the reference splits first)
 __device__ __forceinline__ uint2 mc_key(const McParams& p, int m_local) {
-    uint2 key;
-    if (p.keys_override) key = make_uint2(p.keys_override[2 * m_local], p.keys_override[2 * m_local + 1]);
-    else key = step_particle_key(p.st, p.which_split, (uint32_t)(p.m_offset + m_local), (uint32_t)p.n_particles,
-                                 p.partitionable);
-    if (p.pre_split) key = jax_split_row(key, 1u, 2u, p.partitionable);
-    return key;
+    return make_uint2(p.keys_override[2 * m_local], p.keys_override[2 * m_local + 1]);
 }
 
 // Online-softmax bookkeeping shared by all likelihood kernels. Call by all threads of the CTA.
@@ -118,7 +110,7 @@ __global__ void __launch_bounds__(256) k_mc_lingauss(McParams p) {
     float* sKeep = sX + N * DMAX;           // [N*d] (only if mask)
 
     const bool use_ext = p.g_ext != nullptr;
-    const float alpha = stage_scores(p, m, sBig, sA, HARD, t);
+    const float alpha = stage_scores(p, m, sA, HARD, t);
     const float* throw_ = p.theta + (size_t)m * p.th_ld;
     for (int e = tid; e < d * d; e += blockDim.x) sTh[e] = throw_[e];
     for (int e = tid; e < N * DMAX; e += blockDim.x) {

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) k_mc_bge(McParams p) {
     float* sBig = smem + ((d * d + gpb * d + gpb + 3) & ~3);
 
     const bool use_ext = p.g_ext != nullptr;
-    if (!use_ext) stage_scores(p, m, sBig, sA, true, t);
+    if (!use_ext) stage_scores(p, m, sA, true, t);
     const uint2 key = use_ext ? make_uint2(0, 0) : mc_key(p, m);
     __syncthreads();
 

@@ -52,90 +52,121 @@ template <int DMAX, int MODE>
 __global__ void __launch_bounds__(192, (DMAX <= 20 ? 2 : 1)) k_mc_lin_qr(McParams p, RTri<DMAX> R) {
     extern __shared__ __align__(16) float smem[];
     constexpr bool HARD = (MODE == MC_THETA_HARD || MODE == MC_Z_SCORE);
-    const int d = p.d, gpb = p.gpb;                    // gpb = sample pairs ("slots") per round
+    constexpr int MAT = DMAX * DMAX;                   // all per-(i,j) tables use the compile-time stride DMAX
+    const int d = p.d, dd = d * d, gpb = p.gpb;        // gpb = sample pairs ("slots") per round
     const int m = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
     const int t = p.st ? p.st->t : p.t_override;
     const int S = p.n_samples, Qh = (S + 1) >> 1;      // slot q holds samples q and q + Qh
 
-    float* sA = smem;                       // [d*d]
-    float* sTh = sA + d * d;                // [d*d]
-    float* sLpTh = sTh + d * d;             // [d*d] logN(theta_ij; mean_edge, sig_edge)
-    float* sNode = sLpTh + d * d;           // [2*gpb*d]
-    float* sLpS = sNode + 2 * gpb * d;      // [2*gpb]
-    float* sBig = smem + ((3 * d * d + 2 * gpb * d + 2 * gpb + 3) & ~3);   // Z staging, later the running sums
-    float* sGall = sBig + max(gpb * d * d, 2 * d * p.k);                   // [gpb][2][d][d] graph entries of a round
+    float* sA = smem;                       // [MAT] hard: P_ij; soft tau==1: exp(-alpha s_ij); soft: alpha s_ij
+    float* sTh = sA + MAT;                  // [MAT] theta_ij
+    float* sLpTh = sTh + MAT;               // [MAT] logN(theta_ij; mean_edge, sig_edge)
+    float* sAccAll = sLpTh + MAT;           // [gpb][MAT] softmax-weighted running sums, one private column per thread
+    float* sGall = sAccAll + gpb * MAT;     // [gpb][2][MAT] graph entries of the current round
+    float* sNode = sGall + 2 * gpb * MAT;   // [2*gpb][DMAX] per-node log-probs
+    float* sLpS = sNode + 2 * gpb * DMAX;   // [2*gpb] per-sample log-probs
+    float* sStat = sLpS + 2 * gpb;          // [4] round max, sum exp, sum lp
 
     const bool use_ext = p.g_ext != nullptr;
     const bool fast_soft = !HARD && !use_ext && p.tau == 1.0f;
-    const float alpha = stage_scores(p, m, sBig, sA, HARD, t);
-    const float* throw_ = p.theta + (size_t)m * p.th_ld;
-    for (int e = tid; e < d * d; e += blockDim.x) {
-        const float th = throw_[e];
-        sTh[e] = th;
-        sLpTh[e] = norm_logpdf_pre(th, p.mean_edge, p.sig2_edge, p.lognorm_edge);
-        if (fast_soft) sA[e] = expf(-sA[e]);
+    const float alpha = p.alpha_linear * (float)t;     // dibs.py:70: fp32 product of slope and step
+    {
+        const float* srow = p.scores ? p.scores + (size_t)m * dd : nullptr;
+        const float* throw_ = p.theta + (size_t)m * p.th_ld;
+        const float inv_d_f = 1.0f / (float)d;
+        for (int e = tid; e < dd; e += blockDim.x) {
+            const int i = __float2int_rz(((float)e + 0.5f) * inv_d_f), j = e - i * d;
+            const float a = srow ? alpha * srow[e] : 0.0f;
+            float sa;
+            if (HARD) sa = (i == j) ? 0.0f : sigmoidf_ref(a);             // edge_probs (dibs.py:168-184)
+            else sa = fast_soft ? expf(-a) : a;
+            const float th = throw_[e];
+            sA[i * DMAX + j] = sa;
+            sTh[i * DMAX + j] = th;
+            sLpTh[i * DMAX + j] = norm_logpdf_pre(th, p.mean_edge, p.sig2_edge, p.lognorm_edge);
+        }
     }
     const uint2 key = use_ext ? make_uint2(0, 0) : mc_key(p, m);
-    __syncthreads();
 
     const int slot = tid / d, j = tid - slot * d;
     const bool active = slot < gpb;
     const int q_begin = c * p.s_per_chunk;
     const int q_end = min(Qh, q_begin + p.s_per_chunk);
     const float inv_s2 = 1.0f / p.s2, inv_se2 = 1.0f / p.sig2_edge;
-    const uint32_t n_total = (uint32_t)S * d * d;
-    const uint32_t half = n_total >> 1;
+    const uint32_t half = ((uint32_t)S * dd) >> 1;
+    const float inv_dd = 1.0f / (float)dd, inv_d = 1.0f / (float)d;
 
-    // softmax-weighted running sums live in shared memory (a private slot per thread): sAcc[slot][i*d+j]
-    float* sAcc = sBig + (size_t)slot * d * d + j;
+    float* sAcc = sAccAll + slot * MAT + j;            // sAcc[i*DMAX]
     if (active && MODE != MC_LP_ONLY) {
 #pragma unroll
-        for (int i = 0; i < DMAX; ++i)
-            if (i < d) sAcc[i * d] = 0.0f;
+        for (int i = 0; i < DMAX; ++i) sAcc[i * DMAX] = 0.0f;
     }
     float m_run = -INFINITY, l_run = 0.0f, sum_lp = 0.0f;
+    __syncthreads();
 
     for (int q0 = q_begin; q0 < q_end; q0 += gpb) {
         // ---- phase 1: all threads draw the round's graph entries into shared memory (flat, coalesced)
-        const int dd = d * d;
-        for (int idx = tid; idx < gpb * dd; idx += blockDim.x) {
-            const int sl = idx / dd, ij = idx - sl * dd;
-            const int i = ij / d, jj = ij - i * d;
-            const int qq = q0 + sl;
-            float ga = 0.0f, gb = 0.0f;
-            if (qq < q_end && i != jj) {      // zero_diagonal (utils/func.py:117-125): diagonal draws are discarded
+        const int n_draw = gpb * dd;
+        constexpr int IL = 4;                  // independent threefry chains per thread
+        for (int idx0 = tid; idx0 < n_draw; idx0 += IL * blockDim.x) {
+            uint32_t x0[IL], x1[IL];
+            int off[IL];                       // destination in sGall, or -1
+            float sa[IL];
+            bool draw[IL];
+#pragma unroll
+            for (int u = 0; u < IL; ++u) {
+                const int idx = idx0 + u * blockDim.x;
+                // idx -> (slot, i, j) without integer division (idx < 2^14: the float quotients are exact after +0.5)
+                const int sl = __float2int_rz(((float)idx + 0.5f) * inv_dd), ij = idx - sl * dd;
+                const int i = __float2int_rz(((float)ij + 0.5f) * inv_d), jj = ij - i * d;
+                const int qq = q0 + sl;
+                const bool in = idx < n_draw;
+                off[u] = in ? (2 * sl) * MAT + i * DMAX + jj : -1;
+                // zero_diagonal (utils/func.py:117-125): diagonal draws are discarded
+                draw[u] = in && qq < q_end && i != jj;
+                // legacy threefry layout, S even: flat elements e0 and e0 + n/2 are the two lanes of one block
+                const uint32_t e0 = (uint32_t)qq * dd + ij;
+                x0[u] = e0; x1[u] = e0 + half;
+                sa[u] = draw[u] ? sA[i * DMAX + jj] : 0.0f;
                 if (use_ext) {
-                    ga = p.g_ext[((size_t)m * S + qq) * dd + ij];
-                    if (qq + Qh < S) gb = p.g_ext[((size_t)m * S + qq + Qh) * dd + ij];
-                } else {
-                    // legacy threefry layout, S even: flat elements e0 and e0 + n/2 are the two lanes of one block
-                    const uint32_t e0 = (uint32_t)qq * dd + ij;
-                    const uint2 r = threefry2x32(key.x, key.y, e0, e0 + half);
-                    const float sa = sA[ij];
-                    ga = entry_from_bits<HARD>(r.x, sa, fast_soft, p.tau);
-                    gb = entry_from_bits<HARD>(r.y, sa, fast_soft, p.tau);
+                    float ga = 0.0f, gb = 0.0f;
+                    if (draw[u]) {
+                        ga = p.g_ext[((size_t)m * S + qq) * dd + ij];
+                        if (qq + Qh < S) gb = p.g_ext[((size_t)m * S + qq + Qh) * dd + ij];
+                    }
+                    x0[u] = __float_as_uint(ga); x1[u] = __float_as_uint(gb);
                 }
             }
-            sGall[(size_t)(2 * sl) * dd + ij] = ga;
-            sGall[(size_t)(2 * sl + 1) * dd + ij] = gb;
+            if (!use_ext) threefry2x32_n<IL>(key.x, key.y, x0, x1);
+#pragma unroll
+            for (int u = 0; u < IL; ++u) {
+                if (off[u] < 0) continue;
+                float ga, gb;
+                if (use_ext) { ga = __uint_as_float(x0[u]); gb = __uint_as_float(x1[u]); }
+                else {
+                    ga = draw[u] ? entry_from_bits<HARD>(x0[u], sa[u], fast_soft, p.tau) : 0.0f;
+                    gb = draw[u] ? entry_from_bits<HARD>(x1[u], sa[u], fast_soft, p.tau) : 0.0f;
+                }
+                sGall[off[u]] = ga; sGall[off[u] + MAT] = gb;
+            }
         }
         __syncthreads();
         // ---- phase 2: thread (slot, j) owns column j of the two graphs of its slot
         const int q = q0 + slot;
         const bool v0 = active && q < q_end;
         const bool v1 = v0 && q + Qh < S;
-        const float* sG0 = sGall + (size_t)(2 * slot) * dd + j;     // sG0[i*d] = G_s0[i][j]
-        const float* sG1 = sG0 + dd;
+        const float* sG0 = sGall + (2 * slot) * MAT + j;     // sG0[i*DMAX] = G_s0[i][j]
+        const float* sG1 = sG0 + MAT;
         float u0[DMAX], u1[DMAX];
         float prior0 = 0.0f, prior1 = 0.0f;
 #pragma unroll
         for (int i = 0; i < DMAX; ++i) {
             float ga = 0.0f, gb = 0.0f, th = 0.0f;
             if (v0 && i < d) {
-                ga = sG0[i * d]; gb = sG1[i * d];
-                th = sTh[i * d + j];
+                ga = sG0[i * DMAX]; gb = sG1[i * DMAX];
+                th = sTh[i * DMAX + j];
                 // log p(theta | G): sum g * logN(theta; mean_edge, sig_edge)   (linearGaussian.py:289)
-                const float lpth = sLpTh[i * d + j];
+                const float lpth = sLpTh[i * DMAX + j];
                 prior0 = fmaf(ga, lpth, prior0);
                 prior1 = fmaf(gb, lpth, prior1);
             }
@@ -159,83 +190,90 @@ __global__ void __launch_bounds__(192, (DMAX <= 20 ? 2 : 1)) k_mc_lin_qr(McParam
             ssq1 = fmaf(a1, a1, ssq1);
         }
         // b = Rx^T y (in place, descending columns) = column j of x^T (x - x (G o Theta))
+        if (MODE == MC_THETA_HARD || MODE == MC_Z_REPARAM) {
 #pragma unroll
-        for (int k = DMAX - 1; k >= 0; --k) {
-            float a0 = 0.0f, a1 = 0.0f;
+            for (int k = DMAX - 1; k >= 0; --k) {
+                float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
-            for (int i = 0; i <= k; ++i) {
-                const float r = R.v[rtri_off<DMAX>(i, k)];
-                a0 = fmaf(r, u0[i], a0);
-                a1 = fmaf(r, u1[i], a1);
+                for (int i = 0; i <= k; ++i) {
+                    const float r = R.v[rtri_off<DMAX>(i, k)];
+                    a0 = fmaf(r, u0[i], a0);
+                    a1 = fmaf(r, u1[i], a1);
+                }
+                u0[k] = a0; u1[k] = a1;
             }
-            u0[k] = a0; u1[k] = a1;
         }
         if (v0) {
             const float cst = (float)p.n_obs * p.log2pis2;
-            sNode[(2 * slot) * d + j] = prior0 - 0.5f * (cst + ssq0 * inv_s2);
-            sNode[(2 * slot + 1) * d + j] = prior1 - 0.5f * (cst + ssq1 * inv_s2);
+            sNode[(2 * slot) * DMAX + j] = prior0 - 0.5f * (cst + ssq0 * inv_s2);
+            sNode[(2 * slot + 1) * DMAX + j] = prior1 - 0.5f * (cst + ssq1 * inv_s2);
         }
         __syncthreads();
-        if (tid < 2 * gpb) {
-            const int sl = tid >> 1, wh = tid & 1;
-            const int s = q0 + sl + wh * Qh;
+        // per-sample log-probs and the round's softmax statistics, by warp 0 (2*gpb <= 32 entries)
+        if (tid < 32) {
             float lp = -INFINITY;
-            if (q0 + sl < q_end && s < S) {
-                lp = 0.0f;
-                for (int jj = 0; jj < d; ++jj) lp += sNode[tid * d + jj];
-                if (p.lp_out) p.lp_out[(size_t)m * S + s] = lp;
+            if (tid < 2 * gpb) {
+                const int sl = tid >> 1, wh = tid & 1;
+                const int s = q0 + sl + wh * Qh;
+                if (q0 + sl < q_end && s < S) {
+                    lp = 0.0f;
+                    for (int jj = 0; jj < d; ++jj) lp += sNode[tid * DMAX + jj];
+                    if (p.lp_out) p.lp_out[(size_t)m * S + s] = lp;
+                }
+                sLpS[tid] = lp;
             }
-            sLpS[tid] = lp;
+            if (MODE != MC_LP_ONLY) {
+                const float mx = warp_max(lp);
+                const float ex = (lp == -INFINITY) ? 0.0f : expf(lp - fmaxf(mx, m_run));
+                const float se = warp_sum(ex);
+                const float sl_ = warp_sum(lp == -INFINITY ? 0.0f : lp);
+                if (tid == 0) { sStat[0] = mx; sStat[1] = se; sStat[2] = sl_; }
+            }
         }
         __syncthreads();
         if (MODE != MC_LP_ONLY) {
-            float m_new = m_run;
-            for (int g = 0; g < 2 * gpb; ++g) m_new = fmaxf(m_new, sLpS[g]);
+            const float m_new = fmaxf(m_run, sStat[0]);
             const float scale = (m_run == -INFINITY) ? 0.0f : expf(m_run - m_new);
-            float lsum = 0.0f, lpsum = 0.0f;
-            for (int g = 0; g < 2 * gpb; ++g) {
-                const float lp = sLpS[g];
-                if (lp != -INFINITY) { lsum += expf(lp - m_new); lpsum += lp; }
-            }
-            l_run = l_run * scale + lsum;
-            sum_lp += lpsum;
+            l_run = l_run * scale + sStat[1];
+            sum_lp += sStat[2];
             m_run = m_new;
             const float e0 = v0 ? expf(sLpS[2 * slot] - m_new) : 0.0f;
             const float e1 = v1 ? expf(sLpS[2 * slot + 1] - m_new) : 0.0f;
+            if (v0) {
 #pragma unroll
-            for (int i = 0; i < DMAX; ++i) {
-                float val0 = 0.0f, val1 = 0.0f;
-                if (v0 && i < d) {
-                    const float ga = sG0[i * d], gb = sG1[i * d];
-                    if (MODE == MC_THETA_HARD) {
-                        // d/dtheta: g * (-(theta-mu)/sig^2) + g * (x^T R)/s2          
-                        const float th = sTh[i * d + j];
-                        const float pr = -(th - p.mean_edge) * inv_se2;
-                        val0 = ga * (pr + u0[i] * inv_s2);
-                        val1 = gb * (pr + u1[i] * inv_s2);
-                    } else if (MODE == MC_Z_REPARAM) {
-                        // dS = d lp/dG * tau*alpha*g(1-g)                                (App. B-4, B-6)
-                        const float th = sTh[i * d + j];
-                        const float lpth = sLpTh[i * d + j];
-                        val0 = (lpth + th * u0[i] * inv_s2) * (p.tau * alpha) * ga * (1.0f - ga);
-                        val1 = (lpth + th * u1[i] * inv_s2) * (p.tau * alpha) * gb * (1.0f - gb);
-                    } else {
-                        val0 = ga; val1 = gb;   // score function: weighted mean graph (App. B-2)
+                for (int i = 0; i < DMAX; ++i) {
+                    if (i < d) {
+                        const float ga = sG0[i * DMAX], gb = sG1[i * DMAX];
+                        float val0, val1;
+                        if (MODE == MC_THETA_HARD) {
+                            // d/dtheta: g * (-(theta-mu)/sig^2) + g * (x^T R)/s2          
+                            const float pr = -(sTh[i * DMAX + j] - p.mean_edge) * inv_se2;
+                            val0 = ga * fmaf(u0[i], inv_s2, pr);
+                            val1 = gb * fmaf(u1[i], inv_s2, pr);
+                        } else if (MODE == MC_Z_REPARAM) {
+                            // dS = d lp/dG * tau*alpha*g(1-g)                                (App. B-4, B-6)
+                            const float th = sTh[i * DMAX + j] * inv_s2, lpth = sLpTh[i * DMAX + j];
+                            val0 = fmaf(th, u0[i], lpth) * (p.tau * alpha) * ga * (1.0f - ga);
+                            val1 = fmaf(th, u1[i], lpth) * (p.tau * alpha) * gb * (1.0f - gb);
+                        } else {
+                            val0 = ga; val1 = gb;   // score function: weighted mean graph (App. B-2)
+                        }
+                        sAcc[i * DMAX] = fmaf(sAcc[i * DMAX], scale, fmaf(e0, val0, e1 * val1));
                     }
                 }
-                if (v0 && i < d) sAcc[i * d] = sAcc[i * d] * scale + (e0 * val0 + e1 * val1);
             }
         }
         __syncthreads();
     }
     if (MODE == MC_LP_ONLY) return;
 
-    // deterministic reduction over the slots: sRed[slot][i*d+j]
-    float* sRed = sBig;
+    // deterministic reduction over the slots
     float* out = p.part_acc + ((size_t)m * p.n_chunks + c) * p.acc_size;
-    for (int e = tid; e < d * d; e += blockDim.x) {
+    const float inv_d2 = 1.0f / (float)d;
+    for (int e = tid; e < dd; e += blockDim.x) {
+        const int i = __float2int_rz(((float)e + 0.5f) * inv_d2), jj = e - i * d;
         float sum = 0.0f;
-        for (int g = 0; g < gpb; ++g) sum += sRed[(size_t)g * d * d + e];
+        for (int g = 0; g < gpb; ++g) sum += sAccAll[g * MAT + i * DMAX + jj];
         out[e] = sum;
     }
     if (tid == 0) {
@@ -244,12 +282,9 @@ __global__ void __launch_bounds__(192, (DMAX <= 20 ? 2 : 1)) k_mc_lin_qr(McParam
     }
 }
 
-inline size_t mc_lin_qr_smem(int d, int k, int gpb) {
-    size_t head = (3 * (size_t)d * d + 2 * (size_t)gpb * d + 2 * gpb + 3) & ~(size_t)3;
-    size_t big = (size_t)gpb * d * d;
-    if ((size_t)2 * d * k > big) big = (size_t)2 * d * k;
-    big += (size_t)2 * gpb * d * d;
-    return (head + big + 4) * sizeof(float);
+inline size_t mc_lin_qr_smem(int dmax, int gpb) {
+    size_t mat = (size_t)dmax * dmax;
+    return (3 * mat + (size_t)gpb * mat + 2 * (size_t)gpb * mat + 2 * (size_t)gpb * dmax + 2 * gpb + 8) * sizeof(float);
 }
 
 }  // namespace dibs

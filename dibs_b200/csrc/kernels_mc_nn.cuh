@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) k_mc_nn(McParams p) {
     float* sKeep = sX + N * DMAX;             // [N*d]
 
     const bool use_ext = p.g_ext != nullptr;
-    const float alpha = stage_scores(p, m, sBig, sA, HARD, t);
+    const float alpha = stage_scores(p, m, sA, HARD, t);
     const float* throw_ = p.theta + (size_t)m * p.th_ld;
     for (int e = tid; e < dth; e += blockDim.x) sTh[e] = throw_[e];
     for (int e = tid; e < N * DMAX; e += blockDim.x) {

@@ -16,8 +16,9 @@ struct PairParams {
     int n_all;                           // M
     int row0, n_rows;                    // this rank's rows [row0, row0 + n_rows)
     int dz, dth;
-    int n_split, split_len;              // split of the feature axis for the distance pass
-    float* dist_part;                    // [n_split][2][n_rows][n_all] partial squared distances (z, theta)
+    int n_split, n_split_z;              // feature splits of the distance pass: the first n_split_z cut Z, the rest Theta
+    int split_len_z, split_len_t;        // features per split (multiples of 32)
+    float* dist_part;                    // [n_split][n_rows][n_all] partial squared distances
     float* kz; float* kt; float* kfull;  // [n_rows][n_all]
     float h_z, h_t, scale_z, scale_t;
     // update
@@ -28,78 +29,102 @@ struct PairParams {
     StepState* st; int n_step_splits; int n_particles; int partitionable;   // advanced by block 0 when st != null
 };
 
-// ---- pass 1: partial squared distances, tile 64x64, 256 threads x (4x4), feature axis split across blockIdx.z
-constexpr int KT = 64;   // tile edge
-constexpr int KF = 32;   // features per smem stage
+// ---- pass 1: partial squared distances.  Tile 64 x 64 outputs, 256 threads x (4 x 4) with INTERLEAVED ownership
+// (rows ty + 16a, columns tx + 16b) so that 128-bit shared-memory reads along the feature axis are conflict-free
+// with a row stride of 36 floats.  blockIdx.z = feature split; a split never straddles the Z | Theta boundary
+// (the first n_split_z splits cut the Z features, the rest the Theta features).
+constexpr int KT = 64;    // tile edge
+constexpr int KF = 32;    // features per shared-memory stage
+constexpr int KFP = 36;   // padded row stride (floats): 16-byte aligned, quarter-warp conflict-free
 
 __global__ void __launch_bounds__(256) k_pair_dist(PairParams p) {
-    __shared__ float sI[KF][KT + 1];
-    __shared__ float sJ[KF][KT + 1];
+    __shared__ __align__(16) float sI[KT * KFP];
+    __shared__ __align__(16) float sJ[KT * KFP];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int j0 = blockIdx.x * KT, i0 = blockIdx.y * KT, sp = blockIdx.z;
-    const int D = p.dz + p.dth;
-    const int f_begin = sp * p.split_len, f_end = min(D, f_begin + p.split_len);
-    float accz[4][4], acct[4][4];
+    const bool z_part = sp < p.n_split_z;
+    const int base = z_part ? 0 : p.dz;
+    const int len = z_part ? p.split_len_z : p.split_len_t;
+    const int f_begin = base + (z_part ? sp : sp - p.n_split_z) * len;
+    const int f_end = min(z_part ? p.dz : p.dz + p.dth, f_begin + len);
+    float acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) { accz[a][b] = 0.0f; acct[a][b] = 0.0f; }
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
 
     for (int f0 = f_begin; f0 < f_end; f0 += KF) {
-        // stage KF features of 64 i-rows and 64 j-rows (coalesced along the feature axis)
-        for (int e = tid; e < KT * KF; e += 256) {
-            int r = e / KF, f = e % KF;
-            int fi = f0 + f;
-            bool okf = fi < f_end;
-            int gi = i0 + r, gj = j0 + r;
-            sI[f][r] = (okf && gi < p.n_rows) ? p.x_all[(size_t)(p.row0 + gi) * p.ld + fi] : 0.0f;
-            sJ[f][r] = (okf && gj < p.n_all) ? p.x_all[(size_t)gj * p.ld + fi] : 0.0f;
+        // stage KF features of 64 i-rows and 64 j-rows; a thread copies 2 x float4 per matrix (coalesced along f)
+        for (int e = tid; e < KT * (KF / 4); e += 256) {
+            const int r = e >> 3, f4 = (e & 7) * 4;
+            const int fi = f0 + f4;
+            const int gi = i0 + r, gj = j0 + r;
+            float4 vi = make_float4(0.f, 0.f, 0.f, 0.f), vj = vi;
+            if (gi < p.n_rows) {
+                const float* src = p.x_all + (size_t)(p.row0 + gi) * p.ld + fi;
+                if (fi + 3 < f_end && ((((size_t)(p.row0 + gi) * p.ld + fi) & 3) == 0)) vi = *reinterpret_cast<const float4*>(src);
+                else {
+                    if (fi < f_end) vi.x = src[0];
+                    if (fi + 1 < f_end) vi.y = src[1];
+                    if (fi + 2 < f_end) vi.z = src[2];
+                    if (fi + 3 < f_end) vi.w = src[3];
+                }
+            }
+            if (gj < p.n_all) {
+                const float* src = p.x_all + (size_t)gj * p.ld + fi;
+                if (fi + 3 < f_end && ((((size_t)gj * p.ld + fi) & 3) == 0)) vj = *reinterpret_cast<const float4*>(src);
+                else {
+                    if (fi < f_end) vj.x = src[0];
+                    if (fi + 1 < f_end) vj.y = src[1];
+                    if (fi + 2 < f_end) vj.z = src[2];
+                    if (fi + 3 < f_end) vj.w = src[3];
+                }
+            }
+            *reinterpret_cast<float4*>(&sI[r * KFP + f4]) = vi;
+            *reinterpret_cast<float4*>(&sJ[r * KFP + f4]) = vj;
         }
         __syncthreads();
-        const int nf = min(KF, f_end - f0);
-        for (int f = 0; f < nf; ++f) {
-            const bool is_z = (f0 + f) < p.dz;
-            float xi[4], xj[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) { xi[a] = sI[f][ty * 4 + a]; xj[a] = sJ[f][tx * 4 + a]; }
-            if (is_z) {
+        for (int f4 = 0; f4 < KF; f4 += 4) {
+            float4 xi[4], xj[4];
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 4; ++a) xi[a] = *reinterpret_cast<const float4*>(&sI[(ty + 16 * a) * KFP + f4]);
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) { float df = xi[a] - xj[b]; accz[a][b] = fmaf(df, df, accz[a][b]); }
-            } else {
+            for (int b = 0; b < 4; ++b) xj[b] = *reinterpret_cast<const float4*>(&sJ[(tx + 16 * b) * KFP + f4]);
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) { float df = xi[a] - xj[b]; acct[a][b] = fmaf(df, df, acct[a][b]); }
-            }
+                for (int b = 0; b < 4; ++b) {
+                    float df;
+                    df = xi[a].x - xj[b].x; acc[a][b] = fmaf(df, df, acc[a][b]);
+                    df = xi[a].y - xj[b].y; acc[a][b] = fmaf(df, df, acc[a][b]);
+                    df = xi[a].z - xj[b].z; acc[a][b] = fmaf(df, df, acc[a][b]);
+                    df = xi[a].w - xj[b].w; acc[a][b] = fmaf(df, df, acc[a][b]);
+                }
         }
         __syncthreads();
     }
     const size_t plane = (size_t)p.n_rows * p.n_all;
-    float* oz = p.dist_part + ((size_t)sp * 2) * plane;
-    float* ot = oz + plane;
+    float* o = p.dist_part + (size_t)sp * plane;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            int gi = i0 + ty * 4 + a, gj = j0 + tx * 4 + b;
-            if (gi < p.n_rows && gj < p.n_all) {
-                oz[(size_t)gi * p.n_all + gj] = accz[a][b];
-                ot[(size_t)gi * p.n_all + gj] = acct[a][b];
-            }
+            const int gi = i0 + ty + 16 * a, gj = j0 + tx + 16 * b;
+            if (gi < p.n_rows && gj < p.n_all) o[(size_t)gi * p.n_all + gj] = acc[a][b];
         }
 }
 
 // ---- pass 2: sum the feature splits in fixed order, apply the SE kernels (kernel.py:30,66-71)
 __global__ void __launch_bounds__(256) k_pair_finish(PairParams p) {
     const size_t plane = (size_t)p.n_rows * p.n_all;
+    const int nz = p.n_split_z, nt = p.n_split - p.n_split_z;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < plane; e += (size_t)gridDim.x * blockDim.x) {
         float dz = 0.0f, dt = 0.0f;
-        for (int s = 0; s < p.n_split; ++s) {
-            dz += p.dist_part[((size_t)s * 2) * plane + e];
-            dt += p.dist_part[((size_t)s * 2 + 1) * plane + e];
-        }
+#pragma unroll 4
+        for (int s = 0; s < nz; ++s) dz += p.dist_part[(size_t)s * plane + e];
+#pragma unroll 4
+        for (int s = 0; s < nt; ++s) dt += p.dist_part[(size_t)(nz + s) * plane + e];
         float kz = p.scale_z * expf(-dz / p.h_z);
         float kt = p.dth > 0 ? p.scale_t * expf(-dt / p.h_t) : 0.0f;
         p.kz[e] = kz;
@@ -109,17 +134,20 @@ __global__ void __launch_bounds__(256) k_pair_finish(PairParams p) {
 }
 
 // ---- pass 3: phi_i = -(1/M) sum_j [ K_ij g_j - (2/h) Kterm_ij (x_j - x_i) ]  + optimizer update
-constexpr int PT_I = 32, PT_C = 32, PT_J = 32;   // tile: 32 rows x 32 feature columns, 64 threads x (4x4)
+// Tile: 32 rows x 64 feature columns, 128 threads x (4 rows x 4 columns); per particle j a thread issues four
+// 128-bit shared-memory loads (K, Kterm for its 4 rows; x_j, g_j for its 4 columns) for 48 FP instructions.
+constexpr int PT_I = 32, PT_C = 64, PT_J = 32;
+constexpr int PT_KP = 36;   // padded stride of the transposed K tiles [j][i]
 
-__global__ void __launch_bounds__(64) k_phi_update(PairParams p) {
-    __shared__ float sK[PT_J][PT_I + 1];    // K_full[i][j] transposed: [j][i]
-    __shared__ float sKt[PT_J][PT_I + 1];   // K term (z or theta block)
-    __shared__ float sXj[PT_J][PT_C + 1];
-    __shared__ float sGj[PT_J][PT_C + 1];
-    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+__global__ void __launch_bounds__(128) k_phi_update(PairParams p) {
+    __shared__ __align__(16) float sK[PT_J * PT_KP];     // K_full[i][j] transposed: [j][i]
+    __shared__ __align__(16) float sKt[PT_J * PT_KP];    // K term (z or theta block)
+    __shared__ __align__(16) float sXj[PT_J * PT_C];
+    __shared__ __align__(16) float sGj[PT_J * PT_C];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int i0 = blockIdx.y * PT_I;
     const int D = p.dz + p.dth;
-    // a column tile never straddles the Z | Theta boundary: grid.x = ceil(dz/32) + ceil(dth/32)
+    // a column tile never straddles the Z | Theta boundary: grid.x = ceil(dz/64) + ceil(dth/64)
     const int nzt = (p.dz + PT_C - 1) / PT_C;
     const bool z_block = (int)blockIdx.x < nzt;
     const int c0 = z_block ? blockIdx.x * PT_C : p.dz + ((int)blockIdx.x - nzt) * PT_C;
@@ -138,28 +166,31 @@ __global__ void __launch_bounds__(64) k_phi_update(PairParams p) {
         }
 
     for (int j0 = 0; j0 < p.n_all; j0 += PT_J) {
-        for (int e = tid; e < PT_J * PT_I; e += 64) {
-            int i = e / PT_J, j = e % PT_J;      // coalesced along j (row-major K slab)
+        // K tiles: coalesced along j in global memory, transposed into [j][i]
+        for (int e = tid; e < PT_I * PT_J; e += 128) {
+            int i = e / PT_J, j = e % PT_J;
             int gi = i0 + i, gj = j0 + j;
             bool ok = gi < p.n_rows && gj < p.n_all;
-            sK[j][i] = ok ? p.kfull[(size_t)gi * p.n_all + gj] : 0.0f;
-            sKt[j][i] = ok ? kterm[(size_t)gi * p.n_all + gj] : 0.0f;
+            sK[j * PT_KP + i] = ok ? p.kfull[(size_t)gi * p.n_all + gj] : 0.0f;
+            sKt[j * PT_KP + i] = ok ? kterm[(size_t)gi * p.n_all + gj] : 0.0f;
         }
-        for (int e = tid; e < PT_J * PT_C; e += 64) {
+        for (int e = tid; e < PT_J * PT_C; e += 128) {
             int j = e / PT_C, c = e % PT_C;
             int gj = j0 + j, gc = c0 + c;
             bool ok = gj < p.n_all && gc < c_end;
-            sXj[j][c] = ok ? p.x_all[(size_t)gj * p.ld + gc] : 0.0f;
-            sGj[j][c] = ok ? p.g_all[(size_t)gj * p.g_ld + gc] : 0.0f;
+            sXj[e] = ok ? p.x_all[(size_t)gj * p.ld + gc] : 0.0f;
+            sGj[e] = ok ? p.g_all[(size_t)gj * p.g_ld + gc] : 0.0f;
         }
         __syncthreads();
         const int nj = min(PT_J, p.n_all - j0);
+#pragma unroll 4
         for (int j = 0; j < nj; ++j) {
-            float kf[4], kt[4], xj[4], gj[4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) { kf[a] = sK[j][ty * 4 + a]; kt[a] = sKt[j][ty * 4 + a]; }
-#pragma unroll
-            for (int b = 0; b < 4; ++b) { xj[b] = sXj[j][tx * 4 + b]; gj[b] = sGj[j][tx * 4 + b]; }
+            const float4 kf4 = *reinterpret_cast<const float4*>(&sK[j * PT_KP + ty * 4]);
+            const float4 kt4 = *reinterpret_cast<const float4*>(&sKt[j * PT_KP + ty * 4]);
+            const float4 xj4 = *reinterpret_cast<const float4*>(&sXj[j * PT_C + tx * 4]);
+            const float4 gj4 = *reinterpret_cast<const float4*>(&sGj[j * PT_C + tx * 4]);
+            const float kf[4] = {kf4.x, kf4.y, kf4.z, kf4.w}, kt[4] = {kt4.x, kt4.y, kt4.z, kt4.w};
+            const float xj[4] = {xj4.x, xj4.y, xj4.z, xj4.w}, gj[4] = {gj4.x, gj4.y, gj4.z, gj4.w};
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll

@@ -11,8 +11,53 @@
 
 namespace dibs {
 
+// ------------------------------------------------------------------------------------------
+// step prologue: per particle, the raw scores U V^T (edge-probability pass, dibs.py:179-181) and the sub-keys of
+// every pass of the step (svgd.py:245,251 / 695,699,703 and the pre-draw splits of dibs.py:350,430), so that
+// the Monte-Carlo / acyclicity / assemble kernels neither re-derive keys nor redo the d x k x d contraction.
+// ------------------------------------------------------------------------------------------
+struct PrologueParams {
+    const float* z; int z_ld;
+    int n_local, m_offset, n_particles, d, k;
+    const StepState* st;                 // step loop: keys derive from the loop key ...
+    const uint32_t* keys_in;             // ... hooks: [n_local][2] sub-keys handed in by the caller (n_splits = 1)
+    int n_splits; uint32_t pre_split_mask; int partitionable;
+    float* scores;                       // [n_local][d*d]
+    uint32_t* keys_out;                  // [n_splits][n_local][2]
+};
+
+__global__ void __launch_bounds__(128) k_prologue(PrologueParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int d = p.d, k = p.k, m = blockIdx.x, tid = threadIdx.x;
+    if (tid < p.n_splits && p.keys_out) {
+        uint2 key;
+        if (p.keys_in) key = make_uint2(p.keys_in[2 * m], p.keys_in[2 * m + 1]);
+        else key = step_particle_key(p.st, tid, (uint32_t)(p.m_offset + m), (uint32_t)p.n_particles, p.partitionable != 0);
+        if ((p.pre_split_mask >> tid) & 1u) key = jax_split_row(key, 1u, 2u, p.partitionable != 0);
+        uint32_t* o = p.keys_out + ((size_t)tid * p.n_local + m) * 2;
+        o[0] = key.x; o[1] = key.y;
+    }
+    if (!p.scores) return;
+    // U -> sU[kk][i], V -> sV[kk][j]: de-interleaved and transposed so the contraction reads conflict-free
+    float* sU = smem; float* sV = smem + k * d;
+    const float* zrow = p.z + (size_t)m * p.z_ld;
+    for (int e = tid; e < 2 * d * k; e += blockDim.x) {
+        const int i = e / (2 * k), r = e - i * 2 * k, kk = r >> 1;
+        ((r & 1) ? sV : sU)[kk * d + i] = zrow[e];
+    }
+    __syncthreads();
+    float* out = p.scores + (size_t)m * d * d;
+    for (int e = tid; e < d * d; e += blockDim.x) {
+        const int i = e / d, j = e - i * d;
+        float acc = 0.0f;
+        for (int kk = 0; kk < k; ++kk) acc = fmaf(sU[kk * d + i], sV[kk * d + j], acc);
+        out[e] = acc;
+    }
+}
+
 struct AcycParams {
     const float* z; int z_ld;
+    const float* scores;                 // [n_local][d*d] raw U V^T (k_prologue)
     int n_local, m_offset, n_particles;
     int d, k, n_samples;                 // A
     const StepState* st; int which_split; int partitionable;
@@ -57,19 +102,9 @@ __global__ void __launch_bounds__(256) k_acyclic_grad(AcycParams p) {
     float* bR1 = gbase + 4 * mat;
     float* bAcc = gbase + 5 * mat;                  // per-group accumulator of dS
 
-    const float* zrow = p.z + (size_t)m * p.z_ld;
-    for (int e = tid; e < 2 * d * k; e += blockDim.x) sZ[e] = zrow[e];
-    __syncthreads();
-    for (int e = tid; e < d * d; e += blockDim.x) {
-        int i = e / d, j = e % d;
-        float acc = 0.0f;
-        for (int kk = 0; kk < k; ++kk) acc = fmaf(sZ[(i * k + kk) * 2], sZ[(j * k + kk) * 2 + 1], acc);
-        sS[e] = alpha * acc;
-    }
+    for (int e = tid; e < d * d; e += blockDim.x) sS[e] = alpha * p.scores[(size_t)m * d * d + e];
     for (int e = lane; e < mat; e += gsize) bAcc[e] = 0.0f;
-    uint2 key;
-    if (p.keys_override) key = make_uint2(p.keys_override[2 * m], p.keys_override[2 * m + 1]);
-    else key = step_particle_key(p.st, p.which_split, (uint32_t)(p.m_offset + m), (uint32_t)p.n_particles, p.partitionable);
+    const uint2 key = make_uint2(p.keys_override[2 * m], p.keys_override[2 * m + 1]);
     __syncthreads();
 
     const float inv_d = 1.0f / (float)d;
@@ -171,6 +206,7 @@ __global__ void __launch_bounds__(256) k_acyclic_value(const float* g, int n, in
 // ------------------------------------------------------------------------------------------
 struct AsmParams {
     const float* z; int z_ld;
+    const float* scores;                  // [n_local][d*d] raw U V^T (k_prologue)
     int n_local, d, k;
     const StepState* st; int t_override;
     float alpha_linear, beta_linear;
@@ -217,9 +253,7 @@ __global__ void __launch_bounds__(256) k_assemble_grad(AsmParams p) {
     __syncthreads();
     for (int e = tid; e < d * d; e += blockDim.x) {
         int i = e / d, j = e % d;
-        float acc = 0.0f;
-        for (int kk = 0; kk < k; ++kk) acc = fmaf(sZ[(i * k + kk) * 2], sZ[(j * k + kk) * 2 + 1], acc);
-        sP[e] = (i == j) ? 0.0f : sigmoidf_ref(alpha * acc);
+        sP[e] = (i == j) ? 0.0f : sigmoidf_ref(alpha * p.scores[(size_t)m * d * d + e]);
     }
     __syncthreads();
     if (p.acyc && !p.constraint_only && p.prior_kind == 1 && tid < d) {

@@ -126,7 +126,8 @@ enum {
     DIBS_PHASE_PAIR_DIST = 5,   /* pairwise squared distances (kernel.py:30,66-71)           */
     DIBS_PHASE_PAIR_KERNEL = 6, /* exp -> K                   (kernel.py:30,66-71)           */
     DIBS_PHASE_PHI_UPDATE = 7,  /* phi + optimizer            (svgd.py:194-224,591-670,265)  */
-    DIBS_N_PHASES = 8
+    DIBS_PHASE_STEP_KEYS = 8,   /* per-particle key splits    (svgd.py:245,251,695,699,703)  */
+    DIBS_N_PHASES = 9
 };
 int dibs_svgd_steps_timed(dibs_plan* plan, int32_t t_start, int32_t n_steps, float* z, float* theta,
                           float* v_z, float* v_theta, uint32_t* key, float* sf_baseline, void* stream,

@@ -41,6 +41,29 @@ __global__ void __launch_bounds__(256) k_pipe(float* out, int iters, float a, fl
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// packed fp32x2 FMA (Blackwell FFMA2): 2 FMAs per lane per instruction
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__global__ void __launch_bounds__(256) k_ffma2(float* out, int iters, float a, float b) {
+    unsigned long long x[8];
+    float2 av = make_float2(a, a), bv = make_float2(b, b);
+    const unsigned long long aa = *reinterpret_cast<unsigned long long*>(&av), bb = *reinterpret_cast<unsigned long long*>(&bv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { float2 v = make_float2(a + threadIdx.x * 1e-3f + i, a - i); x[i] = *reinterpret_cast<unsigned long long*>(&v); }
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = ffma2(x[i], aa, bb);
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { float2 v = *reinterpret_cast<float2*>(&x[i]); s += v.x + v.y; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void __launch_bounds__(256) k_dfma(double* out, int iters, double a, double b) {
     double x[8];
 #pragma unroll
@@ -128,6 +151,8 @@ int main() {
     printf(", \"ffma_rcr_tflops\": %.2f", 2 * total / ms / 1e9);
     ms = time_ms([&] { k_pipe<2><<<blocks, threads>>>(out, iters, 1.0001f, 1e-6f, cp); });
     printf(", \"ffma_rc_acc_tflops\": %.2f", 2 * total / ms / 1e9);
+    ms = time_ms([&] { k_ffma2<<<blocks, threads>>>(out, iters, 1.0001f, 1e-6f); });
+    printf(", \"ffma2_tflops\": %.2f", 4 * total / ms / 1e9);
     ms = time_ms([&] { k_dfma<<<blocks, threads>>>((double*)out, iters, 1.0000001, 1e-9); });
     printf(", \"dfma_tflops\": %.2f", 2 * total / ms / 1e9);
     const int tf_iters = 500;
