@@ -129,11 +129,19 @@ struct dibs_plan {
     // pairwise workspace
     int n_split = 1, n_split_z = 1, split_len_z = 0, split_len_t = 0;
     float *dist_part = nullptr, *kz = nullptr, *kt = nullptr, *kfull = nullptr;
+    int n_jsplit = 1, j_len = 0;
+    float* phi_part = nullptr;     // [n_jsplit][M_loc][D]
     // CUDA graphs of one step, per buffer parity
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
     int kernels_per_step = 0;
     bool use_graph = true;
     cudaStream_t cap_stream = nullptr;
+    // fork/join inside a step: the two MC passes, the acyclicity pass and (single GPU) the kernel-matrix pass are
+    // mutually independent, each too small to fill 148 SMs alone -> they run on sibling streams (graph branches)
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork[2] = {nullptr, nullptr};
+    cudaEvent_t ev_join[3] = {nullptr, nullptr, nullptr};
+    bool concurrent = true;
     // NCCL
     NcclComm comm = nullptr;
     // optional per-kernel event timing (dibs_svgd_steps_timed): events recorded after each launch of an eager step
@@ -164,6 +172,15 @@ static int pick_dmax(int d) {
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// CTAs per particle of the acyclicity pass (a function of (A, d, PRNG layout) only)
+constexpr int ACYC_WPC = 4;      // warps (= sample pairs) per CTA of the row-per-lane kernel
+static bool acyc_rows_path(const dibs_plan* p) {
+    return p->d <= 32 && (p->cfg.n_acyclicity_mc_samples % 2) == 0 && !p->cfg.prng_partitionable && !getenv("DIBS_B200_OLD_ACYCLIC");
+}
+static int acyc_chunks(const dibs_plan* p) {
+    return acyc_rows_path(p) ? ceil_div(p->cfg.n_acyclicity_mc_samples / 2, ACYC_WPC) : 1;
+}
+
 extern "C" int dibs_theta_dim(const dibs_plan* plan) { return plan ? plan->Dth : 0; }
 
 // How one Monte-Carlo pass over `n_local` particles x S samples is cut into CTAs.
@@ -173,13 +190,15 @@ struct McShape {
     int chunks;     // CTAs per particle (blockIdx.y)
     int spc;        // samples (or slots) per chunk
     int threads;    // CTA size
+    bool paired;    // BGe: a slot is the sample pair (s, s + S/2)
 };
 
 static bool qr_eligible(int likelihood, int dmax) { return likelihood == DIBS_LIK_LINEAR_GAUSSIAN && dmax <= 32; }
 
-static McShape mc_shape_for(bool qr, int likelihood, int d, int hidden, int n_local, int S) {
+static McShape mc_shape_for(bool qr, int likelihood, int d, int hidden, int n_local, int S, bool pair_ok = false) {
     McShape sh;
     sh.qr = qr;
+    sh.paired = false;
     if (n_local < 1) n_local = 1;
     if (qr) {
         const int Q = (S + 1) / 2;
@@ -255,12 +274,14 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
     p->er_coef = logf(c.er_p) - logf(1.0f - c.er_p);       // NaN / inf for p >= 1 like graph.py:108
     p->sigma_z2 = powf(c.latent_prior_std, 2.0f);           // latent_prior_std ** 2.0 (dibs.py:657)
     if (const char* e = getenv("DIBS_B200_NO_GRAPH")) p->use_graph = !(e[0] == '1');
+    if (const char* e = getenv("DIBS_B200_SERIAL")) p->concurrent = !(e[0] == '1');
 
     const int d = p->d, S = c.n_grad_mc_samples;
     {
         // workspace for the larger of the two possible pass shapes (the QR path is chosen in dibs_set_data)
-        McShape a = mc_shape_for(false, c.likelihood, d, c.hidden, p->M_loc, S);
+        McShape a = mc_shape_for(false, c.likelihood, d, c.hidden, p->M_loc, S, false);
         p->max_chunks = a.chunks;
+
         if (qr_eligible(c.likelihood, p->dmax)) {
             McShape b = mc_shape_for(true, c.likelihood, d, c.hidden, p->M_loc, S);
             if (b.chunks > p->max_chunks) p->max_chunks = b.chunks;
@@ -278,14 +299,14 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
     if ((r = alloc((void**)&p->pk[0], pk_bytes)) || (r = alloc((void**)&p->pk[1], pk_bytes)) ||
         (r = alloc((void**)&p->v, (size_t)p->M_loc * p->D * sizeof(float))) ||
         (r = alloc((void**)&p->base, (size_t)p->M_loc * sizeof(float))) ||
-        (r = alloc((void**)&p->st, sizeof(StepState))) ||
+        (r = alloc((void**)&p->st, 2 * sizeof(StepState))) ||
         (r = alloc((void**)&p->step_keys, (size_t)3 * p->M_loc * 2 * sizeof(uint32_t))) ||
         (r = alloc((void**)&p->scores, (size_t)p->M_loc * p->d * p->d * sizeof(float))) ||
         (r = alloc((void**)&p->z_acc, (size_t)p->M_loc * p->max_chunks * d * d * sizeof(float))) ||
         (r = alloc((void**)&p->z_stats, (size_t)p->M_loc * p->max_chunks * 4 * sizeof(float))) ||
         (r = alloc((void**)&p->th_acc, (size_t)p->M_loc * p->max_chunks * p->th_acc_size * sizeof(float))) ||
         (r = alloc((void**)&p->th_stats, (size_t)p->M_loc * p->max_chunks * 4 * sizeof(float))) ||
-        (r = alloc((void**)&p->acyc, (size_t)p->M_loc * d * d * sizeof(float)))) {
+        (r = alloc((void**)&p->acyc, (size_t)p->M_loc * acyc_chunks(p) * d * d * sizeof(float)))) {
         dibs_plan_destroy(p);
         return r;
     }
@@ -303,9 +324,22 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
         p->split_len_t = p->Dth ? (len < p->Dth ? len : ceil_div(p->Dth, KF) * KF) : KF;
         p->n_split = p->n_split_z + (p->Dth ? ceil_div(p->Dth, p->split_len_t) : 0);
     }
+    // phi: slices of the j axis so that the pass fills the GPU even when a rank owns few rows; the slice length is
+    // a function of (M, D) only -- never of the rank count -- so results are bit-identical for any world size
+    {
+        const int col_tiles = ceil_div(p->Dz, PT_C) + ceil_div(p->Dth, PT_C);
+        const int row_scale = p->M / 256 > 1 ? p->M / 256 : 1;
+        int ns = ceil_div(296, col_tiles * row_scale);
+        const int max_ns = p->M / 64 > 1 ? p->M / 64 : 1;
+        if (ns > max_ns) ns = max_ns;
+        if (ns < 1) ns = 1;
+        p->j_len = ceil_div(ceil_div(p->M, ns), PT_J) * PT_J;
+        p->n_jsplit = ceil_div(p->M, p->j_len);
+    }
     size_t plane = (size_t)p->M_loc * p->M * sizeof(float);
     if ((r = alloc((void**)&p->dist_part, plane * p->n_split)) || (r = alloc((void**)&p->kz, plane)) ||
-        (r = alloc((void**)&p->kt, plane)) || (r = alloc((void**)&p->kfull, plane))) {
+        (r = alloc((void**)&p->kt, plane)) || (r = alloc((void**)&p->kfull, plane)) ||
+        (r = alloc((void**)&p->phi_part, (size_t)p->n_jsplit * p->M_loc * p->D * sizeof(float)))) {
         dibs_plan_destroy(p);
         return r;
     }
@@ -319,8 +353,10 @@ extern "C" int dibs_plan_destroy(dibs_plan* p) {
     for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
     if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
     if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
+    for (int i = 0; i < 3; ++i) { if (p->aux[i]) cudaStreamDestroy(p->aux[i]); if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]); }
+    for (int i = 0; i < 2; ++i) if (p->ev_fork[i]) cudaEventDestroy(p->ev_fork[i]);
     void* ptrs[] = {p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->v, p->base, p->st, p->step_keys, p->scores,
-                    p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->dist_part, p->kz, p->kt, p->kfull};
+                    p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->dist_part, p->kz, p->kt, p->kfull, p->phi_part};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
     return DIBS_OK;
@@ -400,9 +436,11 @@ extern "C" int dibs_set_data(dibs_plan* p, const float* x, const int32_t* mask, 
 // caller (lp_only hook) -- the legacy threefry layout with an even number of samples (two draws per block)
 static McShape mc_shape(const dibs_plan* p, int n_local, int S, bool lp_only) {
     const bool qr = p->use_qr && (lp_only || (!p->cfg.prng_partitionable && (S % 2) == 0));
-    return mc_shape_for(qr, p->cfg.likelihood, p->d, p->cfg.hidden, n_local, S);
+    return mc_shape_for(qr, p->cfg.likelihood, p->d, p->cfg.hidden, n_local, S, !lp_only && !p->cfg.prng_partitionable);
 }
-static void apply_shape(McParams& q, const McShape& sh) { q.n_chunks = sh.chunks; q.s_per_chunk = sh.spc; q.gpb = sh.gpb; }
+static void apply_shape(McParams& q, const McShape& sh) {
+    q.n_chunks = sh.chunks; q.s_per_chunk = sh.spc; q.gpb = sh.gpb; q.paired = sh.paired ? 1 : 0;
+}
 
 struct Src {                 // where the particles of a launch live
     const float* z; int z_ld;
@@ -512,16 +550,16 @@ static int launch_acyc(const dibs_plan* p, const Src& s, int which_split, float*
     a.keys_override = pass_keys(s, which_split); a.t_override = s.t;
     a.alpha_linear = p->cfg.alpha_linear; a.tau = p->cfg.tau; a.ds_out = ds_out;
     const int d = p->d;
-    if (d <= 32 && (a.n_samples % 2) == 0 && !a.partitionable && !getenv("DIBS_B200_OLD_ACYCLIC")) {
+    if (acyc_rows_path(p)) {
         // row-per-lane kernel: a warp per sample pair (both lanes of each threefry block are used)
-        int warps = a.n_samples / 2 < 8 ? a.n_samples / 2 : 8;
+        const int warps = ACYC_WPC;
         size_t smem = acyclic_rows_smem(d, p->k, p->dmax, warps);
-        while (smem > 200 * 1024 && warps > 1) { warps /= 2; smem = acyclic_rows_smem(d, p->k, p->dmax, warps); }
+        dim3 grid(s.n, acyc_chunks(p));
         switch (p->dmax) {
-            case 8: TRY(set_smem(k_acyclic_rows<8>, smem)); k_acyclic_rows<8><<<s.n, warps * 32, smem, stream>>>(a); break;
-            case 16: TRY(set_smem(k_acyclic_rows<16>, smem)); k_acyclic_rows<16><<<s.n, warps * 32, smem, stream>>>(a); break;
-            case 20: TRY(set_smem(k_acyclic_rows<20>, smem)); k_acyclic_rows<20><<<s.n, warps * 32, smem, stream>>>(a); break;
-            default: TRY(set_smem(k_acyclic_rows<32>, smem)); k_acyclic_rows<32><<<s.n, warps * 32, smem, stream>>>(a); break;
+            case 8: TRY(set_smem(k_acyclic_rows<8>, smem)); k_acyclic_rows<8><<<grid, warps * 32, smem, stream>>>(a); break;
+            case 16: TRY(set_smem(k_acyclic_rows<16>, smem)); k_acyclic_rows<16><<<grid, warps * 32, smem, stream>>>(a); break;
+            case 20: TRY(set_smem(k_acyclic_rows<20>, smem)); k_acyclic_rows<20><<<grid, warps * 32, smem, stream>>>(a); break;
+            default: TRY(set_smem(k_acyclic_rows<32>, smem)); k_acyclic_rows<32><<<grid, warps * 32, smem, stream>>>(a); break;
         }
     } else if (d <= 32) {
         int warps = a.n_samples < 8 ? a.n_samples : 8;
@@ -573,18 +611,40 @@ static int launch_prologue(dibs_plan* p, const float* z, int z_ld, int n, int m_
     return DIBS_OK;
 }
 
-// gradient phase for `s.n` particles: MC passes -> acyclicity -> assemble
+// make `to` wait for everything enqueued so far on `from` (a graph edge under stream capture)
+static int stream_edge(cudaStream_t from, cudaStream_t to, cudaEvent_t ev) {
+    CU(cudaEventRecord(ev, from));
+    CU(cudaStreamWaitEvent(to, ev, 0));
+    return DIBS_OK;
+}
+
+static int ensure_aux(dibs_plan* p) {
+    for (int i = 0; i < 3; ++i) {
+        if (!p->aux[i]) CU(cudaStreamCreateWithFlags(&p->aux[i], cudaStreamNonBlocking));
+        if (!p->ev_join[i]) CU(cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 2; ++i) if (!p->ev_fork[i]) CU(cudaEventCreateWithFlags(&p->ev_fork[i], cudaEventDisableTiming));
+    return DIBS_OK;
+}
+
+// gradient phase for `s.n` particles: MC passes | acyclicity (independent: sibling streams when `conc`) -> assemble
 static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_stats, float* z_acc, float* z_stats,
                          float* acyc, const float* base_in, float* base_out, float* grad_z, int gz_ld, float* grad_th,
-                         int gth_ld, cudaStream_t stream) {
+                         int gth_ld, cudaStream_t stream, bool conc) {
     const bool joint = p->cfg.joint;
     const McShape sh = mc_shape(p, s.n, p->cfg.n_grad_mc_samples, false);
     McParams q;
+    cudaStream_t s_th = conc ? p->aux[0] : stream, s_ac = conc ? p->aux[1] : stream;
+    if (conc) {
+        CU(cudaEventRecord(p->ev_fork[1], stream));
+        if (joint) CU(cudaStreamWaitEvent(s_th, p->ev_fork[1], 0));
+        CU(cudaStreamWaitEvent(s_ac, p->ev_fork[1], 0));
+    }
     if (joint) {
         fill_mc(p, s, q);
         q.which_split = 0; q.keys_override = pass_keys(s, 0);
         q.part_acc = th_acc; q.acc_size = p->th_acc_size; q.part_stats = th_stats;
-        TRY(launch_mc<MC_THETA_HARD>(p, q, sh, stream));
+        TRY(launch_mc<MC_THETA_HARD>(p, q, sh, s_th));
         mark(p, stream, DIBS_PHASE_MC_THETA);
     }
     fill_mc(p, s, q);
@@ -593,14 +653,18 @@ static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_st
     if (p->cfg.grad_estimator_z == DIBS_ESTIMATOR_SCORE) TRY(launch_mc<MC_Z_SCORE>(p, q, sh, stream));
     else TRY(launch_mc<MC_Z_REPARAM>(p, q, sh, stream));
     mark(p, stream, DIBS_PHASE_MC_Z);
-    TRY(launch_acyc(p, s, joint ? 2 : 1, acyc, stream));
+    TRY(launch_acyc(p, s, joint ? 2 : 1, acyc, s_ac));
     mark(p, stream, DIBS_PHASE_ACYCLIC);
+    if (conc) {
+        if (joint) TRY(stream_edge(s_th, stream, p->ev_join[0]));
+        TRY(stream_edge(s_ac, stream, p->ev_join[1]));
+    }
     AsmParams a;
     fill_asm(p, s, a);
     a.zacc = z_acc; a.zstats = z_stats; a.z_chunks = sh.chunks;
     a.baselines_in = base_in; a.baselines_out = base_out;
     if (joint) { a.thacc = th_acc; a.thstats = th_stats; a.th_chunks = sh.chunks; a.th_dim = p->Dth; }
-    a.acyc = acyc;
+    a.acyc = acyc; a.acyc_chunks = acyc_chunks(p);
     a.grad_z = grad_z; a.gz_ld = gz_ld; a.grad_th = grad_th; a.gth_ld = gth_ld;
     TRY(launch_asm(p, a, stream));
     mark(p, stream, DIBS_PHASE_ASSEMBLE);
@@ -614,12 +678,19 @@ static void fill_pair(const dibs_plan* p, PairParams& q) {
     q.dist_part = p->dist_part;
     q.kz = p->kz; q.kt = p->Dth ? p->kt : nullptr; q.kfull = p->kfull;
     q.h_z = p->cfg.h_latent; q.h_t = p->cfg.h_theta; q.scale_z = p->cfg.scale_latent; q.scale_t = p->cfg.scale_theta;
-    q.optimizer = p->cfg.optimizer; q.stepsize = p->cfg.stepsize;
-    q.n_particles = p->M; q.partitionable = p->cfg.prng_partitionable;
-    q.n_step_splits = p->cfg.joint ? 3 : 2;
+    q.n_jsplit = p->n_jsplit; q.j_len = p->j_len; q.phi_part = p->phi_part;
 }
 
-static int launch_pair(dibs_plan* p, const PairParams& q, bool with_phi, cudaStream_t stream) {
+static void fill_update(const dibs_plan* p, const PairParams& q, UpdateParams& u) {
+    memset(&u, 0, sizeof(u));
+    u.phi_part = q.phi_part; u.n_jsplit = q.n_jsplit; u.n_rows = q.n_rows; u.dz = q.dz; u.dth = q.dth; u.n_all = q.n_all;
+    u.x_cur = q.x_all + (size_t)q.row0 * q.ld; u.ld = q.ld;
+    u.optimizer = p->cfg.optimizer; u.stepsize = p->cfg.stepsize;
+    u.n_step_splits = p->cfg.joint ? 3 : 2; u.n_particles = p->M; u.partitionable = p->cfg.prng_partitionable;
+    u.d = p->d; u.k = p->k; u.m_offset = p->row0; u.pre_split_mask = p->cfg.joint ? 2u : 1u;
+}
+
+static int launch_kmat(dibs_plan* p, const PairParams& q, cudaStream_t stream) {
     dim3 g1(ceil_div(q.n_all, KT), ceil_div(q.n_rows, KT), q.n_split);
     k_pair_dist<<<g1, 256, 0, stream>>>(q);
     LAUNCHED();
@@ -629,42 +700,64 @@ static int launch_pair(dibs_plan* p, const PairParams& q, bool with_phi, cudaStr
     k_pair_finish<<<blocks, 256, 0, stream>>>(q);
     LAUNCHED();
     mark(p, stream, DIBS_PHASE_PAIR_KERNEL);
-    if (with_phi) {
-        dim3 g3(ceil_div(q.dz, PT_C) + ceil_div(q.dth, PT_C), ceil_div(q.n_rows, PT_I));
-        k_phi_update<<<g3, 128, 0, stream>>>(q);
-        LAUNCHED();
-        mark(p, stream, DIBS_PHASE_PHI_UPDATE);
-    }
     return DIBS_OK;
 }
 
-// one full _svgd_step on the packed buffers; reads pk[cur], writes the updated local rows into pk[cur^1]
-static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream) {
+static int launch_phi(dibs_plan* p, const PairParams& q, cudaStream_t stream) {
+    dim3 g3(ceil_div(q.dz, PT_C) + ceil_div(q.dth, PT_C), ceil_div(q.n_rows, PT_I), q.n_jsplit);
+    k_phi_partial<<<g3, 128, 0, stream>>>(q);
+    LAUNCHED();
+    mark(p, stream, DIBS_PHASE_PHI_UPDATE);
+    return DIBS_OK;
+}
+
+static int launch_update(dibs_plan* p, const UpdateParams& u, cudaStream_t stream) {
+    size_t smem = u.scores ? (size_t)2 * u.d * u.k * sizeof(float) : 0;
+    TRY(set_smem(k_opt_update, smem));
+    k_opt_update<<<u.n_rows, 256, smem, stream>>>(u);
+    LAUNCHED();
+    mark(p, stream, DIBS_PHASE_STEP_KEYS);
+    return DIBS_OK;
+}
+
+// one full _svgd_step on the packed buffers; reads pk[cur], writes the updated local rows into pk[cur^1].
+// The raw scores / sub-keys of the step were produced by the previous step's k_opt_update (or by k_prologue
+// before the first step of a call); the loop state is read from st[cur] and carried into st[cur^1].
+// `conc`: independent passes go to sibling streams (branches of the captured graph); the kernel matrix depends
+// on the particles only, so on a single GPU it overlaps the whole gradient phase.
+static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream, bool conc) {
     float* P = p->pk[cur];
     float* Pn = p->pk[cur ^ 1];
     float* loc = P + (size_t)p->row0 * p->ld;
-    // the z-likelihood estimators split their sub-key before drawing (dibs.py:350,430); theta-grad and the
-    // acyclicity constraint draw with the sub-key itself (dibs.py:510,595)
-    const int n_splits = p->cfg.joint ? 3 : 2;
-    TRY(launch_prologue(p, loc, p->ld, p->M_loc, p->row0, p->st, nullptr, n_splits, p->cfg.joint ? 2u : 1u, p->scores,
-                        p->step_keys, stream));
-    mark(p, stream, DIBS_PHASE_STEP_KEYS);
-    Src s{loc, p->ld, p->Dth ? loc + p->Dz : nullptr, p->ld, p->M_loc, p->row0, p->st, nullptr, 0, p->step_keys, p->scores};
+    StepState* st = p->st + cur;
+    if (conc) TRY(ensure_aux(p));
+    PairParams q;
+    fill_pair(p, q);
+    q.x_all = P; q.ld = p->ld; q.g_all = P + p->D; q.g_ld = p->ld;
+    const bool kmat_early = conc && p->cfg.world_size == 1;
+    if (kmat_early) {
+        TRY(stream_edge(stream, p->aux[2], p->ev_fork[0]));
+        TRY(launch_kmat(p, q, p->aux[2]));
+    }
+    Src s{loc, p->ld, p->Dth ? loc + p->Dz : nullptr, p->ld, p->M_loc, p->row0, st, nullptr, 0, p->step_keys, p->scores};
     TRY(enqueue_grads(p, s, p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->base, p->base,
-                      loc + p->D, p->ld, p->Dth ? loc + p->D + p->Dz : nullptr, p->ld, stream));
+                      loc + p->D, p->ld, p->Dth ? loc + p->D + p->Dz : nullptr, p->ld, stream, conc));
     if (p->cfg.world_size > 1) {
         if (!p->comm) return fail(DIBS_ERR_STATE, "world_size > 1 but no NCCL communicator attached");
         // the one exchange of the step: every rank contributes its rows [Z | Theta | dZ | dTheta] (in place)
         NC(g_nccl.AllGather(loc, P, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm, stream));
         mark(p, stream, DIBS_PHASE_ALLGATHER);
     }
-    PairParams q;
-    fill_pair(p, q);
-    q.x_all = P; q.ld = p->ld; q.g_all = P + p->D; q.g_ld = p->ld;
-    q.x_next = Pn + (size_t)p->row0 * p->ld; q.next_ld = p->ld;
-    q.v = p->v; q.v_ld = p->D;
-    q.st = p->st;
-    TRY(launch_pair(p, q, true, stream));
+    if (kmat_early) TRY(stream_edge(p->aux[2], stream, p->ev_join[2]));
+    else TRY(launch_kmat(p, q, stream));
+    TRY(launch_phi(p, q, stream));
+    UpdateParams u;
+    fill_update(p, q, u);
+    u.x_next = Pn + (size_t)p->row0 * p->ld; u.next_ld = p->ld;
+    u.v = p->v; u.v_ld = p->D;
+    u.st_cur = st; u.st_next = p->st + (cur ^ 1);
+    u.scores = p->scores; u.keys_out = p->step_keys;
+    TRY(launch_update(p, u, stream));
     return DIBS_OK;
 }
 
@@ -695,17 +788,28 @@ static int svgd_steps_impl(dibs_plan* p, int32_t t_start, int32_t n_steps, float
     CU(cudaMemcpyAsync(p->base, sf_baseline, sizeof(float) * p->M_loc, cudaMemcpyDeviceToDevice, stream));
     k_set_state<<<1, 1, 0, stream>>>(p->st, key, t_start);
     LAUNCHED();
+    // scores and sub-keys of the first step; later steps get theirs from the previous step's k_opt_update
+    TRY(launch_prologue(p, loc0, p->ld, p->M_loc, p->row0, p->st, nullptr, p->cfg.joint ? 3 : 2, p->cfg.joint ? 2u : 1u,
+                        p->scores, p->step_keys, stream));
 
-    const bool graph = p->use_graph && p->cfg.world_size == 1 && !(timed && per_kernel);
+    static const bool nccl_graph = !(getenv("DIBS_B200_NCCL_GRAPH") && getenv("DIBS_B200_NCCL_GRAPH")[0] == '0');
+    const bool graph = p->use_graph && (p->cfg.world_size == 1 || nccl_graph) && !(timed && per_kernel);
     p->ev_used = 0;
     if (graph && !p->gexec[0]) {
+        if (p->cfg.world_size > 1) {
+            // warm NCCL up outside the capture (first-use allocations and connection set-up are not capturable);
+            // pk[1] holds nothing yet, so an in-place all-gather on it is harmless
+            if (!p->comm) return fail(DIBS_ERR_STATE, "world_size > 1 but no NCCL communicator attached");
+            NC(g_nccl.AllGather(p->pk[1] + (size_t)p->row0 * p->ld, p->pk[1], (size_t)p->M_loc * p->ld, 7, p->comm, stream));
+            CU(cudaStreamSynchronize(stream));
+        }
         for (int par = 0; par < 2; ++par) {
             long long before = g_launches.load();
             cudaGraph_t g = nullptr;
             // capture on a plan-owned stream (the caller's may be the legacy default stream, which cannot capture)
             if (!p->cap_stream) CU(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
             CU(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
-            int r = enqueue_step(p, par, p->cap_stream);
+            int r = enqueue_step(p, par, p->cap_stream, p->concurrent);
             cudaError_t e = cudaStreamEndCapture(p->cap_stream, &g);
             if (r != DIBS_OK) { if (g) cudaGraphDestroy(g); return r; }
             if (e != cudaSuccess) return fail(DIBS_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
@@ -728,7 +832,7 @@ static int svgd_steps_impl(dibs_plan* p, int32_t t_start, int32_t n_steps, float
             CU(cudaGraphLaunch(p->gexec[cur], stream));
             g_launches.fetch_add(p->kernels_per_step, std::memory_order_relaxed);
         } else {
-            TRY(enqueue_step(p, cur, stream));
+            TRY(enqueue_step(p, cur, stream, p->concurrent && !(timed && per_kernel)));
         }
         if (timed && !per_kernel) { p->timing = true; mark(p, stream, DIBS_N_PHASES); }
         p->timing = false;
@@ -754,7 +858,7 @@ static int svgd_steps_impl(dibs_plan* p, int32_t t_start, int32_t n_steps, float
         if (p->Dth) CU(cudaMemcpy2DAsync(v_theta, ft, p->v + p->Dz, fd, ft, p->M_loc, cudaMemcpyDeviceToDevice, stream));
     }
     CU(cudaMemcpyAsync(sf_baseline, p->base, sizeof(float) * p->M_loc, cudaMemcpyDeviceToDevice, stream));
-    k_get_key<<<1, 1, 0, stream>>>(p->st, key);
+    k_get_key<<<1, 1, 0, stream>>>(p->st + (n_steps & 1), key);
     LAUNCHED();
     return DIBS_OK;
 }
@@ -935,9 +1039,9 @@ static int hook_grads(dibs_plan* p, const float* z, const float* theta, const fl
         a.thacc = acc; a.thstats = stats; a.th_chunks = chunks; a.th_dim = p->Dth;
         a.grad_z = gz_tmp; a.gz_ld = p->Dz; a.grad_th = grad_out; a.gth_ld = p->Dth;
     } else {
-        TRY(sc.get(&acyc, (size_t)n * p->d * p->d));
+        TRY(sc.get(&acyc, (size_t)n * acyc_chunks(p) * p->d * p->d));
         TRY(launch_acyc(p, s, 0, acyc, stream));
-        a.acyc = acyc; a.constraint_only = (what == 3);
+        a.acyc = acyc; a.acyc_chunks = acyc_chunks(p); a.constraint_only = (what == 3);
         a.grad_z = grad_out; a.gz_ld = p->Dz;
     }
     TRY(launch_asm(p, a, stream));
@@ -995,8 +1099,19 @@ static int hook_pair(dibs_plan* p, const float* z, const float* theta, const flo
     if (!k_out) TRY(sc.get(&kf, plane)); else kf = k_out;
     q.dist_part = dist; q.kz = kz; q.kt = p->Dth ? kt : nullptr; q.kfull = kf;
     q.x_all = xs; q.ld = D; q.g_all = gs; q.g_ld = D;
-    if (phi_z) { TRY(sc.get(&phi, (size_t)n * D)); q.phi_out = phi; q.phi_ld = D; }
-    TRY(launch_pair(p, q, phi_z != nullptr, stream));
+    TRY(launch_kmat(p, q, stream));
+    if (phi_z) {
+        TRY(sc.get(&phi, (size_t)n * D));
+        float* part;
+        q.j_len = ceil_div(n, PT_J) * PT_J; q.n_jsplit = 1;
+        TRY(sc.get(&part, (size_t)n * D));
+        q.phi_part = part;
+        TRY(launch_phi(p, q, stream));
+        UpdateParams u;
+        fill_update(p, q, u);
+        u.phi_out = phi; u.phi_ld = D;
+        TRY(launch_update(p, u, stream));
+    }
     if (phi_z) {
         CU(cudaMemcpy2DAsync(phi_z, fz, phi, fd, fz, n, cudaMemcpyDeviceToDevice, stream));
         if (phi_th && p->Dth) CU(cudaMemcpy2DAsync(phi_th, ft, phi + p->Dz, fd, ft, n, cudaMemcpyDeviceToDevice, stream));

@@ -77,7 +77,11 @@ __global__ void __launch_bounds__(256) k_acyclic_rows(AcycParams p) {
 #pragma unroll
     for (int j = 0; j < DMAX; ++j) accT[j] = 0.0f;
 
-    for (int a = warp; a < half_a; a += n_warps) {
+    // blockIdx.y = chunk of n_warps consecutive sample pairs (a fixed decomposition of the A axis: the summation
+    // order never depends on how many particles a rank owns)
+    const int a_begin = blockIdx.y * n_warps;
+    const int a_end = min(half_a, a_begin + n_warps);
+    for (int a = a_begin + warp; a < a_end; a += n_warps) {
         // ---- draw the two soft graphs (samples a and a + A/2) with all lanes
         constexpr int IL = 4;                 // independent threefry chains per lane
         for (int eb = lane; eb < dd; eb += IL * 32) {
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(256) k_acyclic_rows(AcycParams p) {
             if (j < d) sRed[(size_t)warp * dd + j * d + lane] = accT[j];
     }
     __syncthreads();
-    float* outp = p.ds_out + (size_t)m * dd;
+    float* outp = p.ds_out + ((size_t)m * gridDim.y + blockIdx.y) * dd;
     for (int e = tid; e < dd; e += blockDim.x) {
         float sum = 0.0f;
         for (int w = 0; w < n_warps; ++w) sum += sRed[(size_t)w * dd + e];

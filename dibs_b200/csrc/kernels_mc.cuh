@@ -25,6 +25,7 @@ struct McParams {
     int n_particles;                     // M, global
     int d, k, n_obs, n_samples;
     int n_chunks, s_per_chunk, gpb;      // chunking of the MC axis; graphs per block-round
+    int paired;                          // BGe: units are sample pairs (s, s + S/2)
     const float* x;                      // [N, d]
     const int32_t* mask;                 // [N, d] or null
     const StepState* st; int which_split; int partitionable;

@@ -19,14 +19,10 @@ struct PairParams {
     int n_split, n_split_z;              // feature splits of the distance pass: the first n_split_z cut Z, the rest Theta
     int split_len_z, split_len_t;        // features per split (multiples of 32)
     float* dist_part;                    // [n_split][n_rows][n_all] partial squared distances
+    int n_jsplit, j_len;                 // phi: slices of the j axis (j_len on the global index, multiple of 32)
+    float* phi_part;                     // [n_jsplit][n_rows][dz+dth] per-slice sums of drive - (2/h) repulsion
     float* kz; float* kt; float* kfull;  // [n_rows][n_all]
     float h_z, h_t, scale_z, scale_t;
-    // update
-    float* x_next; int next_ld;          // where the updated local rows go (null: phi only)
-    float* v; int v_ld;                  // RMSprop state [n_rows][dz+dth]
-    float* phi_out; int phi_ld;          // optional [n_rows][dz+dth]
-    int optimizer; float stepsize;
-    StepState* st; int n_step_splits; int n_particles; int partitionable;   // advanced by block 0 when st != null
 };
 
 // ---- pass 1: partial squared distances.  Tile 64 x 64 outputs, 256 threads x (4 x 4) with INTERLEAVED ownership
@@ -133,13 +129,15 @@ __global__ void __launch_bounds__(256) k_pair_finish(PairParams p) {
     }
 }
 
-// ---- pass 3: phi_i = -(1/M) sum_j [ K_ij g_j - (2/h) Kterm_ij (x_j - x_i) ]  + optimizer update
+// ---- pass 3: partial sums of phi_i = -(1/M) sum_j [ K_ij g_j - (2/h) Kterm_ij (x_j - x_i) ] over one slice of j.
 // Tile: 32 rows x 64 feature columns, 128 threads x (4 rows x 4 columns); per particle j a thread issues four
 // 128-bit shared-memory loads (K, Kterm for its 4 rows; x_j, g_j for its 4 columns) for 48 FP instructions.
+// blockIdx.z = slice of the j axis (fixed length j_len on the GLOBAL particle index, so the summation order --
+// and with it every bit of the result -- does not depend on how many ranks share the particles).
 constexpr int PT_I = 32, PT_C = 64, PT_J = 32;
 constexpr int PT_KP = 36;   // padded stride of the transposed K tiles [j][i]
 
-__global__ void __launch_bounds__(128) k_phi_update(PairParams p) {
+__global__ void __launch_bounds__(128) k_phi_partial(PairParams p) {
     __shared__ __align__(16) float sK[PT_J * PT_KP];     // K_full[i][j] transposed: [j][i]
     __shared__ __align__(16) float sKt[PT_J * PT_KP];    // K term (z or theta block)
     __shared__ __align__(16) float sXj[PT_J * PT_C];
@@ -154,6 +152,8 @@ __global__ void __launch_bounds__(128) k_phi_update(PairParams p) {
     const int c_end = z_block ? p.dz : D;
     const float* kterm = z_block ? p.kz : p.kt;
     const float h = z_block ? p.h_z : p.h_t;
+    const int j_begin = blockIdx.z * p.j_len;
+    const int j_end = min(p.n_all, j_begin + p.j_len);
 
     float xi[4][4], drive[4][4], rep[4][4];
 #pragma unroll
@@ -165,24 +165,37 @@ __global__ void __launch_bounds__(128) k_phi_update(PairParams p) {
             drive[a][b] = 0.0f; rep[a][b] = 0.0f;
         }
 
-    for (int j0 = 0; j0 < p.n_all; j0 += PT_J) {
+    for (int j0 = j_begin; j0 < j_end; j0 += PT_J) {
         // K tiles: coalesced along j in global memory, transposed into [j][i]
         for (int e = tid; e < PT_I * PT_J; e += 128) {
             int i = e / PT_J, j = e % PT_J;
             int gi = i0 + i, gj = j0 + j;
-            bool ok = gi < p.n_rows && gj < p.n_all;
+            bool ok = gi < p.n_rows && gj < j_end;
             sK[j * PT_KP + i] = ok ? p.kfull[(size_t)gi * p.n_all + gj] : 0.0f;
             sKt[j * PT_KP + i] = ok ? kterm[(size_t)gi * p.n_all + gj] : 0.0f;
         }
-        for (int e = tid; e < PT_J * PT_C; e += 128) {
-            int j = e / PT_C, c = e % PT_C;
-            int gj = j0 + j, gc = c0 + c;
-            bool ok = gj < p.n_all && gc < c_end;
-            sXj[e] = ok ? p.x_all[(size_t)gj * p.ld + gc] : 0.0f;
-            sGj[e] = ok ? p.g_all[(size_t)gj * p.g_ld + gc] : 0.0f;
+        for (int e = tid; e < PT_J * (PT_C / 4); e += 128) {
+            const int j = e / (PT_C / 4), c4 = (e % (PT_C / 4)) * 4;
+            const int gj = j0 + j, gc = c0 + c4;
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
+            if (gj < j_end) {
+                const size_t ox = (size_t)gj * p.ld + gc, og = (size_t)gj * p.g_ld + gc;
+                if (gc + 3 < c_end &&
+                    ((reinterpret_cast<uintptr_t>(p.x_all + ox) | reinterpret_cast<uintptr_t>(p.g_all + og)) & 15) == 0) {
+                    xv = *reinterpret_cast<const float4*>(p.x_all + ox);
+                    gv = *reinterpret_cast<const float4*>(p.g_all + og);
+                } else {
+                    if (gc < c_end) { xv.x = p.x_all[ox]; gv.x = p.g_all[og]; }
+                    if (gc + 1 < c_end) { xv.y = p.x_all[ox + 1]; gv.y = p.g_all[og + 1]; }
+                    if (gc + 2 < c_end) { xv.z = p.x_all[ox + 2]; gv.z = p.g_all[og + 2]; }
+                    if (gc + 3 < c_end) { xv.w = p.x_all[ox + 3]; gv.w = p.g_all[og + 3]; }
+                }
+            }
+            *reinterpret_cast<float4*>(&sXj[j * PT_C + c4]) = xv;
+            *reinterpret_cast<float4*>(&sGj[j * PT_C + c4]) = gv;
         }
         __syncthreads();
-        const int nj = min(PT_J, p.n_all - j0);
+        const int nj = min(PT_J, j_end - j0);
 #pragma unroll 4
         for (int j = 0; j < nj; ++j) {
             const float4 kf4 = *reinterpret_cast<const float4*>(&sK[j * PT_KP + ty * 4]);
@@ -201,37 +214,103 @@ __global__ void __launch_bounds__(128) k_phi_update(PairParams p) {
         }
         __syncthreads();
     }
-    const float inv_m = 1.0f / (float)p.n_all;
+    // weighted_gradient_ascent + repulsion of this j slice   (svgd.py:212-216); the mean and the sign follow in
+    // k_opt_update once all slices are summed
     const float c2 = -2.0f / h;
+    float* part = p.phi_part + (size_t)blockIdx.z * p.n_rows * D;
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            int gi = i0 + ty * 4 + a, gc = c0 + tx * 4 + b;
-            if (gi >= p.n_rows || gc >= c_end) continue;
-            // -(weighted_gradient_ascent + repulsion).mean(axis=0)   (svgd.py:212-216)
-            float phi = -(drive[a][b] + c2 * rep[a][b]) * inv_m;
-            if (p.phi_out) p.phi_out[(size_t)gi * p.phi_ld + gc] = phi;
-            if (p.x_next) {
-                float x = xi[a][b];
-                if (p.optimizer == 1) {
-                    // rmsprop(step, gamma=0.9, eps=1e-8): v = v*gamma + g^2*(1-gamma); x -= step*g/sqrt(v+eps)
-                    float* vp = p.v + (size_t)gi * p.v_ld + gc;
-                    float v = __fadd_rn(__fmul_rn(*vp, 0.9f), __fmul_rn(__fmul_rn(phi, phi), 0.1f));
-                    *vp = v;
-                    x = __fsub_rn(x, __fdiv_rn(__fmul_rn(p.stepsize, phi), __fsqrt_rn(__fadd_rn(v, 1e-8f))));
-                } else {
-                    x = __fsub_rn(x, __fmul_rn(p.stepsize, phi));   // sgd: x - step * g
-                }
-                p.x_next[(size_t)gi * p.next_ld + gc] = x;
-            }
+    for (int a = 0; a < 4; ++a) {
+        const int gi = i0 + ty * 4 + a, gc = c0 + tx * 4;
+        if (gi >= p.n_rows) continue;
+        float* o = part + (size_t)gi * D + gc;
+        const float v0 = fmaf(c2, rep[a][0], drive[a][0]), v1 = fmaf(c2, rep[a][1], drive[a][1]);
+        const float v2 = fmaf(c2, rep[a][2], drive[a][2]), v3 = fmaf(c2, rep[a][3], drive[a][3]);
+        if (gc + 3 < c_end && ((((size_t)blockIdx.z * p.n_rows + gi) * D + gc) & 3) == 0) {
+            *reinterpret_cast<float4*>(o) = make_float4(v0, v1, v2, v3);
+        } else {
+            if (gc < c_end) o[0] = v0;
+            if (gc + 1 < c_end) o[1] = v1;
+            if (gc + 2 < c_end) o[2] = v2;
+            if (gc + 3 < c_end) o[3] = v3;
         }
-    // carry the loop state: key <- after this step's (M+1)-way splits, t <- t + 1   (svgd.py:245,251,272)
-    if (p.st && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
-        uint2 key = make_uint2(p.st->key[0], p.st->key[1]);
+    }
+}
+
+// ---- pass 4: per particle, sum the j slices in fixed order -> phi, optimizer step, and -- because the whole new
+// latent row is in shared memory at that point -- the NEXT step's prologue: raw scores U V^T and per-pass sub-keys
+// (see k_prologue).  Block 0 also carries the loop state into the other StepState slot.
+struct UpdateParams {
+    const float* phi_part; int n_jsplit;      // [n_jsplit][n_rows][D]
+    int n_rows, dz, dth, n_all;
+    const float* x_cur; int ld;               // this rank's rows of the current packed buffer
+    float* x_next; int next_ld;               // updated rows (null: phi only)
+    float* v; int v_ld;
+    float* phi_out; int phi_ld;
+    int optimizer; float stepsize;
+    const StepState* st_cur; StepState* st_next;
+    int n_step_splits, n_particles, partitionable;
+    // next-step prologue (scores null: skip)
+    int d, k, m_offset; uint32_t pre_split_mask;
+    float* scores; uint32_t* keys_out;
+};
+
+__global__ void __launch_bounds__(256) k_opt_update(UpdateParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int m = blockIdx.x, tid = threadIdx.x;
+    const int D = p.dz + p.dth, d = p.d, k = p.k;
+    float* sU = smem; float* sV = smem + k * d;       // new Z, de-interleaved and transposed: sU[kk][i], sV[kk][j]
+    // loop state: key <- after this step's (M+1)-way splits, t <- t + 1   (svgd.py:245,251,272)
+    if (p.st_cur && tid < 32) {
+        uint2 key = make_uint2(p.st_cur->key[0], p.st_cur->key[1]);
         for (int w = 0; w < p.n_step_splits; ++w) key = jax_split_row(key, 0u, (uint32_t)p.n_particles + 1u, p.partitionable);
-        p.st->key[0] = key.x; p.st->key[1] = key.y;
-        p.st->t += 1;
+        if (p.keys_out && tid < p.n_step_splits) {
+            uint2 sk = key;
+            for (int w = 0; w < tid; ++w) sk = jax_split_row(sk, 0u, (uint32_t)p.n_particles + 1u, p.partitionable != 0);
+            sk = jax_split_row(sk, (uint32_t)(p.m_offset + m) + 1u, (uint32_t)p.n_particles + 1u, p.partitionable != 0);
+            if ((p.pre_split_mask >> tid) & 1u) sk = jax_split_row(sk, 1u, 2u, p.partitionable != 0);
+            uint32_t* o = p.keys_out + ((size_t)tid * p.n_rows + m) * 2;
+            o[0] = sk.x; o[1] = sk.y;
+        }
+        if (m == 0 && tid == 0) {
+            p.st_next->key[0] = key.x; p.st_next->key[1] = key.y;
+            p.st_next->t = p.st_cur->t + 1; p.st_next->pad = 0;
+        }
+    }
+    const float inv_m = 1.0f / (float)p.n_all;
+    const size_t plane = (size_t)p.n_rows * D;
+    const float* part = p.phi_part + (size_t)m * D;
+    for (int e = tid; e < D; e += blockDim.x) {
+        float sum = 0.0f;
+        for (int s = 0; s < p.n_jsplit; ++s) sum += part[(size_t)s * plane + e];
+        // -(weighted_gradient_ascent + repulsion).mean(axis=0)   (svgd.py:212-216)
+        const float phi = -sum * inv_m;
+        if (p.phi_out) p.phi_out[(size_t)m * p.phi_ld + e] = phi;
+        float x = p.x_cur[(size_t)m * p.ld + e];
+        if (p.x_next) {
+            if (p.optimizer == 1) {
+                // rmsprop(step, gamma=0.9, eps=1e-8): v = v*gamma + g^2*(1-gamma); x -= step*g/sqrt(v+eps)
+                float* vp = p.v + (size_t)m * p.v_ld + e;
+                float v = __fadd_rn(__fmul_rn(*vp, 0.9f), __fmul_rn(__fmul_rn(phi, phi), 0.1f));
+                *vp = v;
+                x = __fsub_rn(x, __fdiv_rn(__fmul_rn(p.stepsize, phi), __fsqrt_rn(__fadd_rn(v, 1e-8f))));
+            } else {
+                x = __fsub_rn(x, __fmul_rn(p.stepsize, phi));   // sgd: x - step * g
+            }
+            p.x_next[(size_t)m * p.next_ld + e] = x;
+        }
+        if (p.scores && e < p.dz) {
+            const int i = e / (2 * k), r = e - i * 2 * k, kk = r >> 1;
+            ((r & 1) ? sV : sU)[kk * d + i] = x;
+        }
+    }
+    if (!p.scores) return;
+    __syncthreads();
+    float* out = p.scores + (size_t)m * d * d;
+    for (int e = tid; e < d * d; e += blockDim.x) {
+        const int i = e / d, j = e - i * d;
+        float acc = 0.0f;
+        for (int kk = 0; kk < k; ++kk) acc = fmaf(sU[kk * d + i], sV[kk * d + j], acc);
+        out[e] = acc;
     }
 }
 

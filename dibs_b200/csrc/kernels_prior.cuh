@@ -218,7 +218,8 @@ struct AsmParams {
     // theta partials
     const float* thacc; const float* thstats; int th_chunks; int th_dim;
     // prior
-    const float* acyc; int n_acyc;        // [n_local][d*d] sums over A samples; null = skip prior terms entirely
+    const float* acyc; int n_acyc;        // [n_local][acyc_chunks][d*d] sums over A samples; null = skip prior terms entirely
+    int acyc_chunks;
     int constraint_only;                  // hook: return mean_a grad h alone (no beta, no other terms)
     int prior_kind; float er_coef;        // log p - log(1-p)
     float sigma_z2;                       // latent_prior_std ** 2
@@ -284,7 +285,9 @@ __global__ void __launch_bounds__(256) k_assemble_grad(AsmParams p) {
                 ds += (p.z_mode == MC_Z_SCORE) ? base_fac * alpha * (w - pe) : w;
             }
             if (p.acyc) {
-                float ac = p.acyc[(size_t)m * d * d + e] / (float)p.n_acyc;    // .mean(0)  (dibs.py:601)
+                float acs = 0.0f;
+                for (int c = 0; c < p.acyc_chunks; ++c) acs += p.acyc[((size_t)m * p.acyc_chunks + c) * d * d + e];
+                float ac = acs / (float)p.n_acyc;    // .mean(0)  (dibs.py:601)
                 if (p.constraint_only) ds += ac;
                 else {
                     ds -= beta * ac;
