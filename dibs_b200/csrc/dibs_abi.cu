@@ -69,6 +69,7 @@ struct NcclApi {
     int (*GetUniqueId)(NcclId*) = nullptr;
     int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
     int (*CommDestroy)(NcclComm) = nullptr;
+    int (*CommAbort)(NcclComm) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -84,6 +85,7 @@ static int nccl_load() {
     g_nccl.GetUniqueId = (int (*)(NcclId*))dlsym(lib, "ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(NcclComm*, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
     g_nccl.CommDestroy = (int (*)(NcclComm))dlsym(lib, "ncclCommDestroy");
+    g_nccl.CommAbort = (int (*)(NcclComm))dlsym(lib, "ncclCommAbort");
     g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))dlsym(lib, "ncclAllGather");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy)
@@ -351,7 +353,13 @@ extern "C" int dibs_plan_destroy(dibs_plan* p) {
     if (!p) return DIBS_OK;
     for (int i = 0; i < 2; ++i) if (p->gexec[i]) cudaGraphExecDestroy(p->gexec[i]);
     for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
-    if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
+    if (p->comm) {
+        // plans are torn down whenever the host garbage-collects them, not at a point all ranks agree on: abort is
+        // the non-collective teardown (ncclCommDestroy may wait for the peers); nothing is in flight after the sync
+        cudaDeviceSynchronize();
+        if (g_nccl.CommAbort) g_nccl.CommAbort(p->comm);
+        else if (g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
+    }
     if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
     for (int i = 0; i < 3; ++i) { if (p->aux[i]) cudaStreamDestroy(p->aux[i]); if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]); }
     for (int i = 0; i < 2; ++i) if (p->ev_fork[i]) cudaEventDestroy(p->ev_fork[i]);
