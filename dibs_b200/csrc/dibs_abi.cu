@@ -220,7 +220,20 @@ static McShape mc_shape_for(bool qr, int likelihood, int d, int hidden, int n_lo
         sh.spc = rpc * best;
         return sh;
     }
-    int per_item = (likelihood == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN) ? d * nn_hp(hidden) : d;
+    if (likelihood == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN) {
+        // one slot (sample pair when the PRNG layout allows, else one sample) at a time per CTA; chunks of slots
+        sh.paired = pair_ok && (S % 2) == 0;
+        const int Q = sh.paired ? S / 2 : S;
+        int want = ceil_div(4 * 148, n_local);
+        if (want > Q) want = Q;
+        if (want < 1) want = 1;
+        sh.spc = ceil_div(Q, want);
+        sh.chunks = ceil_div(Q, sh.spc);
+        sh.gpb = 1;
+        sh.threads = nn_threads(d, hidden);
+        return sh;
+    }
+    int per_item = d;
     int gpb = 256 / per_item; if (gpb < 1) gpb = 1; if (gpb > S) gpb = S;
     sh.gpb = gpb;
     sh.threads = 256;
@@ -283,6 +296,10 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
         // workspace for the larger of the two possible pass shapes (the QR path is chosen in dibs_set_data)
         McShape a = mc_shape_for(false, c.likelihood, d, c.hidden, p->M_loc, S, false);
         p->max_chunks = a.chunks;
+        {
+            McShape b = mc_shape_for(false, c.likelihood, d, c.hidden, p->M_loc, S, true);
+            if (b.chunks > p->max_chunks) p->max_chunks = b.chunks;
+        }
 
         if (qr_eligible(c.likelihood, p->dmax)) {
             McShape b = mc_shape_for(true, c.likelihood, d, c.hidden, p->M_loc, S);
@@ -525,7 +542,7 @@ static int launch_mc(const dibs_plan* p, McParams q, const McShape& sh, cudaStre
     if (lik == DIBS_LIK_LINEAR_GAUSSIAN) {
         smem = mc_lingauss_smem(p->d, p->k, p->N, q.gpb, p->dmax, q.mask != nullptr);
     } else if (lik == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN) {
-        smem = mc_nn_smem(p->d, p->k, p->N, q.gpb, p->dmax, q.hidden, q.hp, q.mask != nullptr);
+        smem = mc_nn_smem(p->d, p->N, p->dmax, q.hidden, q.mask != nullptr);
     } else {
         if (MODE != MC_Z_SCORE && MODE != MC_LP_ONLY) return fail(DIBS_ERR_UNSUPPORTED, "BGe supports the score estimator only");
         smem = mc_bge_smem(p->d, p->k, q.gpb);
@@ -596,7 +613,7 @@ static void fill_asm(const dibs_plan* p, const Src& s, AsmParams& a) {
 }
 
 static int launch_asm(const dibs_plan* p, const AsmParams& a, cudaStream_t stream) {
-    size_t smem = assemble_smem(p->d, p->k);
+    size_t smem = assemble_smem(p->d, p->k, a.z_chunks, a.th_chunks);
     TRY(set_smem(k_assemble_grad, smem));
     k_assemble_grad<<<a.n_local, 256, smem, stream>>>(a);
     LAUNCHED();
@@ -638,7 +655,7 @@ static int ensure_aux(dibs_plan* p) {
 // gradient phase for `s.n` particles: MC passes | acyclicity (independent: sibling streams when `conc`) -> assemble
 static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_stats, float* z_acc, float* z_stats,
                          float* acyc, const float* base_in, float* base_out, float* grad_z, int gz_ld, float* grad_th,
-                         int gth_ld, cudaStream_t stream, bool conc) {
+                         int gth_ld, cudaStream_t stream, bool conc, uint32_t* next_keys, StepState* st_next) {
     const bool joint = p->cfg.joint;
     const McShape sh = mc_shape(p, s.n, p->cfg.n_grad_mc_samples, false);
     McParams q;
@@ -674,6 +691,9 @@ static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_st
     if (joint) { a.thacc = th_acc; a.thstats = th_stats; a.th_chunks = sh.chunks; a.th_dim = p->Dth; }
     a.acyc = acyc; a.acyc_chunks = acyc_chunks(p);
     a.grad_z = grad_z; a.gz_ld = gz_ld; a.grad_th = grad_th; a.gth_ld = gth_ld;
+    a.next_keys = next_keys; a.st_next = st_next;
+    a.n_step_splits = joint ? 3 : 2; a.n_particles = p->M; a.partitionable = p->cfg.prng_partitionable;
+    a.m_offset = s.m_offset; a.pre_split_mask = joint ? 2u : 1u;
     TRY(launch_asm(p, a, stream));
     mark(p, stream, DIBS_PHASE_ASSEMBLE);
     return DIBS_OK;
@@ -694,8 +714,7 @@ static void fill_update(const dibs_plan* p, const PairParams& q, UpdateParams& u
     u.phi_part = q.phi_part; u.n_jsplit = q.n_jsplit; u.n_rows = q.n_rows; u.dz = q.dz; u.dth = q.dth; u.n_all = q.n_all;
     u.x_cur = q.x_all + (size_t)q.row0 * q.ld; u.ld = q.ld;
     u.optimizer = p->cfg.optimizer; u.stepsize = p->cfg.stepsize;
-    u.n_step_splits = p->cfg.joint ? 3 : 2; u.n_particles = p->M; u.partitionable = p->cfg.prng_partitionable;
-    u.d = p->d; u.k = p->k; u.m_offset = p->row0; u.pre_split_mask = p->cfg.joint ? 2u : 1u;
+    u.d = p->d; u.k = p->k;
 }
 
 static int launch_kmat(dibs_plan* p, const PairParams& q, cudaStream_t stream) {
@@ -749,7 +768,8 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream, bool conc) {
     }
     Src s{loc, p->ld, p->Dth ? loc + p->Dz : nullptr, p->ld, p->M_loc, p->row0, st, nullptr, 0, p->step_keys, p->scores};
     TRY(enqueue_grads(p, s, p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->base, p->base,
-                      loc + p->D, p->ld, p->Dth ? loc + p->D + p->Dz : nullptr, p->ld, stream, conc));
+                      loc + p->D, p->ld, p->Dth ? loc + p->D + p->Dz : nullptr, p->ld, stream, conc, p->step_keys,
+                      p->st + (cur ^ 1)));
     if (p->cfg.world_size > 1) {
         if (!p->comm) return fail(DIBS_ERR_STATE, "world_size > 1 but no NCCL communicator attached");
         // the one exchange of the step: every rank contributes its rows [Z | Theta | dZ | dTheta] (in place)
@@ -763,8 +783,7 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream, bool conc) {
     fill_update(p, q, u);
     u.x_next = Pn + (size_t)p->row0 * p->ld; u.next_ld = p->ld;
     u.v = p->v; u.v_ld = p->D;
-    u.st_cur = st; u.st_next = p->st + (cur ^ 1);
-    u.scores = p->scores; u.keys_out = p->step_keys;
+    u.scores = p->scores;
     TRY(launch_update(p, u, stream));
     return DIBS_OK;
 }
@@ -1007,6 +1026,7 @@ extern "C" int dibs_log_joint_prob(dibs_plan* p, const float* g, const float* th
     q.n_samples = n_samples; q.g_ext = g; q.lp_out = lp_out;
     McShape sh = mc_shape(p, n, n_samples, true);
     sh.chunks = 1; sh.spc = sh.qr ? (n_samples + 1) / 2 : n_samples;     // one CTA per particle, all samples
+    sh.paired = false;
     TRY(launch_mc<MC_LP_ONLY>(p, q, sh, stream));
     CU(cudaStreamSynchronize(stream));
     return DIBS_OK;

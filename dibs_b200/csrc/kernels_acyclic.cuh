@@ -17,27 +17,29 @@
 
 namespace dibs {
 
-// out[j] = sum_k x[k] * Zs[k][j]   (Zs row-major, leading dimension DMAX, zero-padded)
+// out[j] = sum_k x[k] * Zs[k][j]   (Zs row-major, leading dimension DMAX, zero-padded); packed FFMA2: the row of Z
+// arrives as 128-bit broadcasts = two register pairs, x[k] is duplicated into a pair once per k
 template <int DMAX>
 __device__ __forceinline__ void row_times_smem(const float (&x)[DMAX], const float* __restrict__ Zs, int d,
                                                float (&out)[DMAX]) {
+    f32x2 o2[DMAX / 2];
 #pragma unroll
-    for (int j = 0; j < DMAX; ++j) out[j] = 0.0f;
+    for (int j = 0; j < DMAX / 2; ++j) o2[j] = 0ull;
 #pragma unroll
     for (int k = 0; k < DMAX; ++k) {
         if (k < d) {
-            const float xk = x[k];
-            const float4* zr = reinterpret_cast<const float4*>(Zs + k * DMAX);
+            const f32x2 xk = pack2(x[k], x[k]);
+            const ulonglong2* zr = reinterpret_cast<const ulonglong2*>(Zs + k * DMAX);
 #pragma unroll
             for (int q = 0; q < DMAX / 4; ++q) {
-                const float4 z = zr[q];
-                out[4 * q] = fmaf(xk, z.x, out[4 * q]);
-                out[4 * q + 1] = fmaf(xk, z.y, out[4 * q + 1]);
-                out[4 * q + 2] = fmaf(xk, z.z, out[4 * q + 2]);
-                out[4 * q + 3] = fmaf(xk, z.w, out[4 * q + 3]);
+                const ulonglong2 z = zr[q];
+                o2[2 * q] = fma2(xk, z.x, o2[2 * q]);
+                o2[2 * q + 1] = fma2(xk, z.y, o2[2 * q + 1]);
             }
         }
     }
+#pragma unroll
+    for (int j = 0; j < DMAX / 2; ++j) { out[2 * j] = lo2(o2[j]); out[2 * j + 1] = hi2(o2[j]); }
 }
 
 template <int DMAX>

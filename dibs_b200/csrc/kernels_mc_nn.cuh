@@ -2,49 +2,76 @@
 //
 // replaces: dibs/models/nonlinearGaussian.py:248-326 (log_prob_parameters, log_likelihood,
 // interventional_log_joint_prob; stax Dense -> Relu -> Dense(1) per node, nonlinearGaussian.py:35-81,116-135)
-// under the estimators of dibs/inference/dibs.py:395-459,488-551.
-//
-// thread = (sample s, node j, hidden unit h); the HP = 2^ceil(log2 H) lanes of one (s, j) share the node's
-// mean through warp shuffles.  Closed forms: SURVEY App. B-7.
+// under the estimators of dibs/inference/dibs.py:395-459,488-551.  Closed forms: SURVEY App. B-7.
 // theta layout per particle: W1[j,i,h] | b1[j,h] | W2[j,h] | b2[j].
+//
+// Work decomposition: CTA = (particle, chunk of sample slots); a slot is the sample pair (s, s + S/2) -- the two
+// lanes of one threefry block in JAX's legacy layout -- or a single sample.  Per slot the CTA draws the graph
+// entries with a flat thread mapping (both lanes of every block used), then thread = (node j, hidden unit h):
+// JPW = 32 / H nodes per warp, the H lanes of a node adjacent, so the node mean is H warp shuffles.  The thread
+// keeps its masked first-layer weights w[i] = G_ij W1[j,i,h] and their gradient in registers as PACKED PAIRS and
+// streams the N observations from shared memory as 128-bit broadcasts, two observations per iteration:
+// 5 LDS.128 + 20 FFMA2 per observation at d = 20.
 #pragma once
 #include "common.cuh"
 #include "kernels_mc.cuh"
+#include "kernels_mc_lin_qr.cuh"   // entry_from_bits
 
 namespace dibs {
 
 static inline int nn_hp(int h) { int p = 1; while (p < h) p <<= 1; return p; }
+static inline int nn_jpw(int h) { return 32 / h; }                                 // nodes per warp
+static inline int nn_threads(int d, int h) { return ((d + nn_jpw(h) - 1) / nn_jpw(h)) * 32; }
+
+// CTA size = 32 * ceil(d / (32 / H)); the bound below is what the launcher checks against
+template <int DMAX> constexpr int nn_max_threads() { return DMAX <= 32 ? 256 : (DMAX <= 64 ? 384 : 768); }
 
 template <int DMAX, int MODE>
-__global__ void __launch_bounds__(256) k_mc_nn(McParams p) {
+__global__ void __launch_bounds__(nn_max_threads<DMAX>()) k_mc_nn(McParams p) {
     extern __shared__ __align__(16) float smem[];
     constexpr bool HARD = (MODE == MC_THETA_HARD || MODE == MC_Z_SCORE);
-    const int d = p.d, N = p.n_obs, gpb = p.gpb, H = p.hidden, HP = p.hp;
-    const int m = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+    constexpr int NP = DMAX / 2;                  // packed pairs per row
+    const int d = p.d, dd = d * d, N = p.n_obs, H = p.hidden;
+    const int m = blockIdx.x, c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t = p.st ? p.st->t : p.t_override;
+    const int S = p.n_samples;
+    const bool paired = p.paired != 0;
+    const int per = paired ? 2 : 1;
+    const int Qh = paired ? (S >> 1) : S;
     const int dth = d * (d * H + 2 * H + 1);
-    const int oB1 = d * d * H, oW2 = oB1 + d * H, oB2 = oW2 + d * H;
+    const int oB1 = dd * H, oW2 = oB1 + d * H, oB2 = oW2 + d * H;
+    const int JPW = 32 / H;
 
-    float* sA = smem;                         // [d*d]
-    float* sCnt = sA + d * d;                 // [d]
-    float* sNode = sCnt + d;                  // [gpb*d]
-    float* sLpS = sNode + gpb * d;            // [gpb]
-    float* sG = sLpS + gpb;                   // [gpb*d*d]: sG[(s_local*d + j)*d + i]
-    float* sTh = smem + ((d * d + d + gpb * d + gpb + gpb * d * d + 3) & ~3);   // [dth]
-    float* sBig = sTh + ((dth + 3) & ~3);
-    float* sX = sBig;                         // [N*DMAX]
-    float* sKeep = sX + N * DMAX;             // [N*d]
+    float* sA = smem;                                    // [dd] hard: P_ij; soft tau==1: exp(-alpha s_ij); soft: alpha s_ij
+    float* sG = sA + ((dd + 3) & ~3);                    // [2][dd] graph entries of the slot, [i*d + j]
+    float* sNode = sG + ((2 * dd + 3) & ~3);             // [d] per-node log-probs of the current sample
+    float* sCnt = sNode + ((d + 3) & ~3);                // [d] unmasked observation count per node
+    float* sTh = sCnt + ((d + 3) & ~3);                  // [dth]
+    float* sX = sTh + ((dth + 3) & ~3);                  // [N][DMAX] zero-padded rows
+    float* sKeep = sX + (size_t)N * DMAX;                // [N*d] (only if mask)
 
     const bool use_ext = p.g_ext != nullptr;
-    const float alpha = stage_scores(p, m, sA, HARD, t);
-    const float* throw_ = p.theta + (size_t)m * p.th_ld;
-    for (int e = tid; e < dth; e += blockDim.x) sTh[e] = throw_[e];
-    for (int e = tid; e < N * DMAX; e += blockDim.x) {
-        int n = e / DMAX, i = e % DMAX;
-        sX[e] = i < d ? p.x[n * d + i] : 0.0f;
+    const bool fast_soft = !HARD && !use_ext && p.tau == 1.0f;
+    const float alpha = p.alpha_linear * (float)t;       // dibs.py:70
+    {
+        const float* srow = p.scores ? p.scores + (size_t)m * dd : nullptr;
+        for (int e = tid; e < dd; e += blockDim.x) {
+            const int i = e / d, j = e - i * d;
+            const float a = srow ? alpha * srow[e] : 0.0f;
+            float sa;
+            if (HARD) sa = (i == j) ? 0.0f : sigmoidf_ref(a);             // edge_probs (dibs.py:168-184)
+            else sa = fast_soft ? expf(-a) : a;
+            sA[e] = sa;
+        }
+        const float* throw_ = p.theta + (size_t)m * p.th_ld;
+        for (int e = tid; e < dth; e += blockDim.x) sTh[e] = throw_[e];
+        for (int e = tid; e < N * DMAX; e += blockDim.x) {
+            const int n = e / DMAX, i = e - n * DMAX;
+            sX[e] = i < d ? p.x[n * d + i] : 0.0f;
+        }
+        if (p.mask)
+            for (int e = tid; e < N * d; e += blockDim.x) sKeep[e] = p.mask[e] ? 0.0f : 1.0f;
     }
-    if (p.mask)
-        for (int e = tid; e < N * d; e += blockDim.x) sKeep[e] = p.mask[e] ? 0.0f : 1.0f;
     __syncthreads();
     if (tid < d) {
         float cnt = (float)N;
@@ -52,18 +79,24 @@ __global__ void __launch_bounds__(256) k_mc_nn(McParams p) {
         sCnt[tid] = cnt;
     }
     const uint2 key = use_ext ? make_uint2(0, 0) : mc_key(p, m);
-    __syncthreads();
 
-    const int per_graph = d * HP;
-    const bool active = tid < gpb * per_graph;
-    const int s_local = tid / per_graph, j = (tid % per_graph) / HP, h = tid % HP;
-    const bool hact = h < H;
-    const int s_begin = c * p.s_per_chunk;
-    const int s_end = min(p.n_samples, s_begin + p.s_per_chunk);
+    // thread -> (node j, hidden unit h)
+    const int jl = lane / H, h = lane - jl * H;
+    const int j = warp * JPW + jl;
+    const bool on = jl < JPW && j < d;                   // lanes beyond JPW*H and nodes beyond d idle (carry zeros)
+    const int jj = on ? j : 0;
+    const int base_lane = jl * H;                        // first lane of this node's group
     const float inv_s2 = 1.0f / p.s2;
-    const float inv_sp2 = 1.0f / p.sig2_edge;   // sig_param^2 (fill_mc maps the NN prior onto these fields)
-    // lanes of one (s, j) group are contiguous and HP | 32, so a group never straddles a warp
-    const unsigned gmask = HP == 32 ? 0xffffffffu : (((1u << HP) - 1u) << ((tid & 31) / HP * HP));
+    const float inv_sp2 = 1.0f / p.sig2_edge;            // sig_param^2 (fill_mc maps the NN prior onto these fields)
+    const float w2 = on ? sTh[oW2 + jj * H + h] : 0.0f;
+    const float b1 = on ? sTh[oB1 + jj * H + h] : 0.0f;
+    const float b2 = on ? sTh[oB2 + jj] : 0.0f;
+    // parameter prior terms that do not depend on the graph (nonlinearGaussian.py:257-276)
+    float prior_fix = 0.0f;
+    if (on) {
+        prior_fix = norm_logpdf_pre(b1, 0.0f, p.sig2_edge, p.lognorm_edge) + norm_logpdf_pre(w2, 0.0f, p.sig2_edge, p.lognorm_edge);
+        if (h == 0) prior_fix += norm_logpdf_pre(b2, 0.0f, p.sig2_edge, p.lognorm_edge);
+    }
 
     float acc[DMAX];
 #pragma unroll
@@ -71,157 +104,158 @@ __global__ void __launch_bounds__(256) k_mc_nn(McParams p) {
     float acc_b1 = 0.0f, acc_w2 = 0.0f, acc_b2 = 0.0f;
     float m_run = -INFINITY, l_run = 0.0f, sum_lp = 0.0f;
 
-    for (int s0 = s_begin; s0 < s_end; s0 += gpb) {
-        const int s = s0 + s_local;
-        const bool valid = active && s < s_end;
-        // the HP lanes of a group split the column's d draws, then share it through shared memory
-        if (valid) {
-            for (int i = h; i < d; i += HP) {
-                float g = use_ext ? (i == j ? 0.0f : p.g_ext[(((size_t)m * p.n_samples + s) * d + i) * d + j])
-                                  : graph_entry<HARD>(p, key, sA, s, i, j, d, p.tau);
-                sG[(s_local * d + j) * d + i] = g;
-            }
-        }
-        __syncwarp();
-        float w[DMAX], gw[DMAX];
-        float gb1 = 0.0f, gw2 = 0.0f, gb2 = 0.0f, ssq = 0.0f, prior = 0.0f;
-        float w2 = 0.0f, b1 = 0.0f, b2 = 0.0f;
-        if (valid) {
-            w2 = hact ? sTh[oW2 + j * H + h] : 0.0f;
-            b1 = hact ? sTh[oB1 + j * H + h] : 0.0f;
-            b2 = sTh[oB2 + j];
-#pragma unroll
-            for (int i = 0; i < DMAX; ++i) {
-                float wv = 0.0f;
-                if (i < d && hact) {
-                    float g = sG[(s_local * d + j) * d + i];
-                    float w1 = sTh[(j * d + i) * H + h];
-                    wv = g * w1;
-                    // first-layer weights masked by G[i,j] in the prior (nonlinearGaussian.py:264-266)
-                    prior = fmaf(g, norm_logpdf_pre(w1, 0.0f, p.sig2_edge, p.lognorm_edge), prior);
+    const int q_begin = c * p.s_per_chunk;
+    const int q_end = min(Qh, q_begin + p.s_per_chunk);
+    const uint32_t n_total = (uint32_t)S * dd;
+    const uint32_t half = n_total >> 1;
+    __syncthreads();
+
+    for (int q = q_begin; q < q_end; ++q) {
+        // ---- draw the slot's graph entries (flat mapping, coalesced shared-memory writes)
+        for (int e = tid; e < dd; e += blockDim.x) {
+            const int i = e / d, je = e - i * d;
+            float g0 = 0.0f, g1 = 0.0f;
+            if (i != je) {                                // zero_diagonal: diagonal draws are discarded
+                if (use_ext) {
+                    g0 = p.g_ext[((size_t)m * S + q) * dd + e];
+                } else if (paired) {
+                    const uint32_t e0 = (uint32_t)q * dd + e;
+                    const uint2 bits = threefry2x32(key.x, key.y, e0, e0 + half);
+                    const float sa = sA[e];
+                    g0 = entry_from_bits<HARD>(bits.x, sa, fast_soft, p.tau);
+                    g1 = entry_from_bits<HARD>(bits.y, sa, fast_soft, p.tau);
+                } else {
+                    const uint32_t bits = jax_bits(key, (uint32_t)q * dd + e, n_total, p.partitionable);
+                    g0 = entry_from_bits<HARD>(bits, sA[e], fast_soft, p.tau);
                 }
-                w[i] = wv; gw[i] = 0.0f;
             }
-            if (hact) prior += norm_logpdf_pre(b1, 0.0f, p.sig2_edge, p.lognorm_edge) +
-                               norm_logpdf_pre(w2, 0.0f, p.sig2_edge, p.lognorm_edge);
-            if (h == 0) prior += norm_logpdf_pre(b2, 0.0f, p.sig2_edge, p.lognorm_edge);
-        } else {
-#pragma unroll
-            for (int i = 0; i < DMAX; ++i) { w[i] = 0.0f; gw[i] = 0.0f; }
-        }
-        // all lanes of the warp run the loop (shuffles); invalid lanes carry zeros
-        for (int n = 0; n < N; ++n) {
-            const float4* xr = reinterpret_cast<const float4*>(sX + n * DMAX);
-            float xv[DMAX];
-#pragma unroll
-            for (int q = 0; q < DMAX / 4; ++q) {
-                float4 v = xr[q];
-                xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
-            }
-            float pre = b1;
-#pragma unroll
-            for (int i = 0; i < DMAX; ++i) pre = fmaf(xv[i], w[i], pre);
-            const float act = fmaxf(pre, 0.0f);
-            float part = act * w2;
-            for (int o = HP >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(gmask, part, o);
-            const float mean = part + b2;
-            float r = valid ? sX[n * DMAX + j] - mean : 0.0f;
-            if (p.mask && valid) r *= sKeep[n * d + j];
-            ssq = fmaf(r, r, ssq);
-            const float delta = r * inv_s2;
-            const float dpre = (pre > 0.0f) ? delta * w2 : 0.0f;
-#pragma unroll
-            for (int i = 0; i < DMAX; ++i) gw[i] = fmaf(xv[i], dpre, gw[i]);
-            gb1 += dpre; gw2 = fmaf(delta, act, gw2); gb2 += delta;
-        }
-        for (int o = HP >> 1; o > 0; o >>= 1) prior += __shfl_xor_sync(gmask, prior, o);
-        if (valid && h == 0) sNode[s_local * d + j] = prior - 0.5f * (sCnt[j] * p.log2pis2 + ssq * inv_s2);
-        __syncthreads();
-        if (tid < gpb) {
-            float lp = -INFINITY;
-            if (s0 + tid < s_end) {
-                lp = 0.0f;
-                for (int jj = 0; jj < d; ++jj) lp += sNode[tid * d + jj];
-                if (p.lp_out) p.lp_out[(size_t)m * p.n_samples + s0 + tid] = lp;
-            }
-            sLpS[tid] = lp;
+            sG[e] = g0; sG[dd + e] = g1;
         }
         __syncthreads();
-        if (MODE != MC_LP_ONLY) {
-            float m_new = m_run;
-            for (int g = 0; g < gpb; ++g) m_new = fmaxf(m_new, sLpS[g]);
-            const float scale = (m_run == -INFINITY) ? 0.0f : expf(m_run - m_new);
-            float lsum = 0.0f, lpsum = 0.0f;
-            for (int g = 0; g < gpb; ++g) {
-                float lp = sLpS[g];
-                if (lp != -INFINITY) { lsum += expf(lp - m_new); lpsum += lp; }
-            }
-            l_run = l_run * scale + lsum;
-            sum_lp += lpsum;
-            m_run = m_new;
-            const bool on = valid && hact;
-            const float e = on ? expf(sLpS[s_local] - m_new) : 0.0f;
+#pragma unroll 1
+        for (int hs = 0; hs < per; ++hs) {
+            const int s = q + hs * Qh;
+            const float* G = sG + hs * dd;
+            // masked first-layer weights of (j, h) and the graph-dependent prior term
+            f32x2 w[NP], gw[NP];
+            float prior = prior_fix;
 #pragma unroll
-            for (int i = 0; i < DMAX; ++i) {
-                float val = 0.0f;
-                if (on && i < d) {
-                    float g = sG[(s_local * d + j) * d + i];
-                    float w1 = sTh[(j * d + i) * H + h];
-                    if (MODE == MC_THETA_HARD) {
-                        val = g * (gw[i] - w1 * inv_sp2);                       // dW1[j,i,h]
-                    } else if (MODE == MC_Z_REPARAM) {
-                        float dg = gw[i] * w1 + norm_logpdf_pre(w1, 0.0f, p.sig2_edge, p.lognorm_edge);   // this h's share of d lp/dG[i,j]
-                        val = dg * (p.tau * alpha) * g * (1.0f - g);
-                    } else {
-                        val = (h == 0) ? g : 0.0f;
+            for (int ip = 0; ip < NP; ++ip) {
+                float wv[2] = {0.0f, 0.0f};
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int i = 2 * ip + u;
+                    if (on && i < d) {
+                        const float g = G[i * d + jj];
+                        const float w1 = sTh[(jj * d + i) * H + h];
+                        wv[u] = g * w1;
+                        // first-layer weights masked by G[i,j] in the prior (nonlinearGaussian.py:264-266)
+                        prior = fmaf(g, norm_logpdf_pre(w1, 0.0f, p.sig2_edge, p.lognorm_edge), prior);
                     }
                 }
-                acc[i] = acc[i] * scale + e * val;
+                w[ip] = pack2(wv[0], wv[1]);
+                gw[ip] = 0ull;
             }
-            if (MODE == MC_THETA_HARD) {
-                acc_b1 = acc_b1 * scale + e * (gb1 - b1 * inv_sp2);
-                acc_w2 = acc_w2 * scale + e * (gw2 - w2 * inv_sp2);
-                acc_b2 = acc_b2 * scale + ((on && h == 0) ? e * (gb2 - b2 * inv_sp2) : 0.0f);
+            float gb1 = 0.0f, gw2 = 0.0f, gb2 = 0.0f, ssq = 0.0f;
+            // ---- forward + backward over the observations, two per iteration (independent chains)
+            for (int n0 = 0; n0 < N; n0 += 2) {
+                const bool two = n0 + 1 < N;
+                const ulonglong2* xa = reinterpret_cast<const ulonglong2*>(sX + (size_t)n0 * DMAX);
+                const ulonglong2* xb = reinterpret_cast<const ulonglong2*>(sX + (size_t)(two ? n0 + 1 : n0) * DMAX);
+                f32x2 xva[NP], xvb[NP];
+#pragma unroll
+                for (int qd = 0; qd < DMAX / 4; ++qd) {
+                    const ulonglong2 va = xa[qd], vb = xb[qd];
+                    xva[2 * qd] = va.x; xva[2 * qd + 1] = va.y;
+                    xvb[2 * qd] = vb.x; xvb[2 * qd + 1] = vb.y;
+                }
+                f32x2 pa = pack2(b1, 0.0f), pb = pa;
+#pragma unroll
+                for (int ip = 0; ip < NP; ++ip) { pa = fma2(xva[ip], w[ip], pa); pb = fma2(xvb[ip], w[ip], pb); }
+                const float pre_a = lo2(pa) + hi2(pa), pre_b = lo2(pb) + hi2(pb);
+                const float act_a = fmaxf(pre_a, 0.0f), act_b = fmaxf(pre_b, 0.0f);
+                const float part_a = act_a * w2, part_b = act_b * w2;
+                float mean_a = b2, mean_b = b2;
+                for (int hh = 0; hh < H; ++hh) {
+                    mean_a += __shfl_sync(0xffffffffu, part_a, base_lane + hh);
+                    mean_b += __shfl_sync(0xffffffffu, part_b, base_lane + hh);
+                }
+                float ra = on ? sX[(size_t)n0 * DMAX + jj] - mean_a : 0.0f;
+                float rb = (on && two) ? sX[(size_t)(n0 + 1) * DMAX + jj] - mean_b : 0.0f;
+                if (p.mask && on) { ra *= sKeep[n0 * d + jj]; if (two) rb *= sKeep[(n0 + 1) * d + jj]; }
+                ssq = fmaf(ra, ra, ssq); ssq = fmaf(rb, rb, ssq);
+                const float da = ra * inv_s2, db = rb * inv_s2;
+                const float dpa = (pre_a > 0.0f) ? da * w2 : 0.0f;
+                const float dpb = (pre_b > 0.0f) ? db * w2 : 0.0f;
+                const f32x2 dpa2 = pack2(dpa, dpa), dpb2 = pack2(dpb, dpb);
+#pragma unroll
+                for (int ip = 0; ip < NP; ++ip) { gw[ip] = fma2(xva[ip], dpa2, gw[ip]); gw[ip] = fma2(xvb[ip], dpb2, gw[ip]); }
+                gb1 += dpa + dpb; gw2 = fmaf(da, act_a, gw2); gw2 = fmaf(db, act_b, gw2); gb2 += da + db;
             }
+            // node log-prob: prior terms of the group's lanes + Gaussian likelihood
+            float psum = 0.0f;
+            for (int hh = 0; hh < H; ++hh) psum += __shfl_sync(0xffffffffu, prior, base_lane + hh);
+            if (on && h == 0) sNode[j] = psum - 0.5f * (sCnt[j] * p.log2pis2 + ssq * inv_s2);
+            __syncthreads();
+            float lp = 0.0f;
+            for (int q2 = 0; q2 < d; ++q2) lp += sNode[q2];                  // every thread: same fixed order
+            if (p.lp_out && tid == 0) p.lp_out[(size_t)m * S + s] = lp;
+            if (MODE != MC_LP_ONLY) {
+                const float m_new = fmaxf(m_run, lp);
+                const float scale = (m_run == -INFINITY) ? 0.0f : expf(m_run - m_new);
+                const float e = expf(lp - m_new);
+                l_run = l_run * scale + e;
+                sum_lp += lp;
+                m_run = m_new;
+                const float ew = on ? e : 0.0f;
+#pragma unroll
+                for (int i = 0; i < DMAX; ++i) {
+                    float val = 0.0f;
+                    if (on && i < d) {
+                        const float g = G[i * d + jj];
+                        const float w1 = sTh[(jj * d + i) * H + h];
+                        const float gwi = (i & 1) ? hi2(gw[i >> 1]) : lo2(gw[i >> 1]);
+                        if (MODE == MC_THETA_HARD) {
+                            val = g * (gwi - w1 * inv_sp2);                      // dW1[j,i,h]
+                        } else if (MODE == MC_Z_REPARAM) {
+                            // this h's share of d lp/dG[i,j], through the sigmoid (App. B-4, B-7)
+                            const float dg = gwi * w1 + norm_logpdf_pre(w1, 0.0f, p.sig2_edge, p.lognorm_edge);
+                            val = dg * (p.tau * alpha) * g * (1.0f - g);
+                        } else {
+                            val = (h == 0) ? g : 0.0f;
+                        }
+                    }
+                    acc[i] = fmaf(acc[i], scale, ew * val);
+                }
+                if (MODE == MC_THETA_HARD) {
+                    acc_b1 = fmaf(acc_b1, scale, ew * (gb1 - b1 * inv_sp2));
+                    acc_w2 = fmaf(acc_w2, scale, ew * (gw2 - w2 * inv_sp2));
+                    acc_b2 = fmaf(acc_b2, scale, (h == 0) ? ew * (gb2 - b2 * inv_sp2) : 0.0f);
+                }
+            }
+            __syncthreads();                                                    // sNode is rewritten by the next sample
         }
-        __syncthreads();
     }
     if (MODE == MC_LP_ONLY) return;
 
     float* out = p.part_acc + ((size_t)m * p.n_chunks + c) * p.acc_size;
-    float* sRed = sBig;
     if (MODE == MC_THETA_HARD) {
-        // sRed[s_local][theta index]
-        if (active && hact) {
-            float* r = sRed + (size_t)s_local * dth;
+        // one thread per (j, h): the chunk's sums go straight to the partial buffer
+        if (on) {
 #pragma unroll
             for (int i = 0; i < DMAX; ++i)
-                if (i < d) r[(j * d + i) * H + h] = acc[i];
-            r[oB1 + j * H + h] = acc_b1;
-            r[oW2 + j * H + h] = acc_w2;
-            if (h == 0) r[oB2 + j] = acc_b2;
-        }
-        __syncthreads();
-        for (int e = tid; e < dth; e += blockDim.x) {
-            float sum = 0.0f;
-            for (int g = 0; g < gpb; ++g) sum += sRed[(size_t)g * dth + e];
-            out[e] = sum;
+                if (i < d) out[(j * d + i) * H + h] = acc[i];
+            out[oB1 + j * H + h] = acc_b1;
+            out[oW2 + j * H + h] = acc_w2;
+            if (h == 0) out[oB2 + j] = acc_b2;
         }
     } else {
-        // fold the hidden-unit lanes first (fixed shuffle tree), then the sample slots
+        // dS[i][j] = sum over the hidden units of the node (fixed order)
 #pragma unroll
-        for (int i = 0; i < DMAX; ++i)
-            for (int o = HP >> 1; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(gmask, acc[i], o);
-        if (active && h == 0) {
-#pragma unroll
-            for (int i = 0; i < DMAX; ++i)
-                if (i < d) sRed[(size_t)s_local * d * d + i * d + j] = acc[i];
-        }
-        __syncthreads();
-        for (int e = tid; e < d * d; e += blockDim.x) {
+        for (int i = 0; i < DMAX; ++i) {
             float sum = 0.0f;
-            for (int g = 0; g < gpb; ++g) sum += sRed[(size_t)g * d * d + e];
-            out[e] = sum;
+            for (int hh = 0; hh < H; ++hh) sum += __shfl_sync(0xffffffffu, acc[i], base_lane + hh);
+            if (on && h == 0 && i < d) out[i * d + j] = sum;
         }
     }
     if (tid == 0) {
@@ -230,16 +264,12 @@ __global__ void __launch_bounds__(256) k_mc_nn(McParams p) {
     }
 }
 
-inline size_t mc_nn_smem(int d, int k, int n_obs, int gpb, int dmax, int H, int HP, bool has_mask) {
-    size_t dth = (size_t)d * (d * H + 2 * H + 1);
-    size_t head = ((size_t)d * d + d + (size_t)gpb * d + gpb + (size_t)gpb * d * d + 3) & ~(size_t)3;
-    head += (dth + 3) & ~(size_t)3;
-    size_t big = (size_t)n_obs * dmax + (has_mask ? (size_t)n_obs * d : 0);
-    size_t red = (size_t)gpb * (dth > (size_t)d * d ? dth : (size_t)d * d);
-    size_t zz = (size_t)2 * d * k;
-    if (red > big) big = red;
-    if (zz > big) big = zz;
-    return (head + big + 4) * sizeof(float);
+inline size_t mc_nn_smem(int d, int n_obs, int dmax, int H, bool has_mask) {
+    const size_t dd = (size_t)d * d;
+    const size_t dth = (size_t)d * (d * H + 2 * H + 1);
+    size_t f = ((dd + 3) & ~(size_t)3) + ((2 * dd + 3) & ~(size_t)3) + 2 * (((size_t)d + 3) & ~(size_t)3) + ((dth + 3) & ~(size_t)3);
+    f += (size_t)n_obs * dmax + (has_mask ? (size_t)n_obs * d : 0);
+    return (f + 4) * sizeof(float);
 }
 
 }  // namespace dibs

@@ -43,11 +43,12 @@ __global__ void __launch_bounds__(256) k_pair_dist(PairParams p) {
     const int len = z_part ? p.split_len_z : p.split_len_t;
     const int f_begin = base + (z_part ? sp : sp - p.n_split_z) * len;
     const int f_end = min(z_part ? p.dz : p.dz + p.dth, f_begin + len);
-    float acc[4][4];
+    // accumulators are packed pairs {sum over even features, sum over odd features} (FFMA2), folded at the end
+    f32x2 acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0ull;
 
     for (int f0 = f_begin; f0 < f_end; f0 += KF) {
         // stage KF features of 64 i-rows and 64 j-rows; a thread copies 2 x float4 per matrix (coalesced along f)
@@ -82,20 +83,18 @@ __global__ void __launch_bounds__(256) k_pair_dist(PairParams p) {
         __syncthreads();
 #pragma unroll
         for (int f4 = 0; f4 < KF; f4 += 4) {
-            float4 xi[4], xj[4];
+            ulonglong2 xi[4], xj[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) xi[a] = *reinterpret_cast<const float4*>(&sI[(ty + 16 * a) * KFP + f4]);
+            for (int a = 0; a < 4; ++a) xi[a] = *reinterpret_cast<const ulonglong2*>(&sI[(ty + 16 * a) * KFP + f4]);
 #pragma unroll
-            for (int b = 0; b < 4; ++b) xj[b] = *reinterpret_cast<const float4*>(&sJ[(tx + 16 * b) * KFP + f4]);
+            for (int b = 0; b < 4; ++b) xj[b] = *reinterpret_cast<const ulonglong2*>(&sJ[(tx + 16 * b) * KFP + f4]);
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    float df;
-                    df = xi[a].x - xj[b].x; acc[a][b] = fmaf(df, df, acc[a][b]);
-                    df = xi[a].y - xj[b].y; acc[a][b] = fmaf(df, df, acc[a][b]);
-                    df = xi[a].z - xj[b].z; acc[a][b] = fmaf(df, df, acc[a][b]);
-                    df = xi[a].w - xj[b].w; acc[a][b] = fmaf(df, df, acc[a][b]);
+                    f32x2 df;
+                    df = sub2(xi[a].x, xj[b].x); acc[a][b] = fma2(df, df, acc[a][b]);
+                    df = sub2(xi[a].y, xj[b].y); acc[a][b] = fma2(df, df, acc[a][b]);
                 }
         }
         __syncthreads();
@@ -107,7 +106,7 @@ __global__ void __launch_bounds__(256) k_pair_dist(PairParams p) {
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int gi = i0 + ty + 16 * a, gj = j0 + tx + 16 * b;
-            if (gi < p.n_rows && gj < p.n_all) o[(size_t)gi * p.n_all + gj] = acc[a][b];
+            if (gi < p.n_rows && gj < p.n_all) o[(size_t)gi * p.n_all + gj] = lo2(acc[a][b]) + hi2(acc[a][b]);
         }
 }
 
@@ -138,8 +137,10 @@ constexpr int PT_I = 32, PT_C = 64, PT_J = 32;
 constexpr int PT_KP = 36;   // padded stride of the transposed K tiles [j][i]
 
 __global__ void __launch_bounds__(128) k_phi_partial(PairParams p) {
-    __shared__ __align__(16) float sK[PT_J * PT_KP];     // K_full[i][j] transposed: [j][i]
-    __shared__ __align__(16) float sKt[PT_J * PT_KP];    // K term (z or theta block)
+    // K tiles transposed to [j][i] with every entry DUPLICATED ({k, k}): the packed FFMA2 needs the row weight in
+    // both halves of a register pair, and two 128-bit loads are cheaper than four register moves per (j, row)
+    __shared__ __align__(16) float sK[PT_J * PT_KP * 2];     // K_full
+    __shared__ __align__(16) float sKt[PT_J * PT_KP * 2];    // K term (z or theta block)
     __shared__ __align__(16) float sXj[PT_J * PT_C];
     __shared__ __align__(16) float sGj[PT_J * PT_C];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -155,14 +156,17 @@ __global__ void __launch_bounds__(128) k_phi_partial(PairParams p) {
     const int j_begin = blockIdx.z * p.j_len;
     const int j_end = min(p.n_all, j_begin + p.j_len);
 
-    float xi[4][4], drive[4][4], rep[4][4];
+    f32x2 xi[4][2], drive[4][2], rep[4][2];      // [row][column pair]
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            int gi = i0 + ty * 4 + a, gc = c0 + tx * 4 + b;
-            xi[a][b] = (gi < p.n_rows && gc < c_end) ? p.x_all[(size_t)(p.row0 + gi) * p.ld + gc] : 0.0f;
-            drive[a][b] = 0.0f; rep[a][b] = 0.0f;
+        for (int b = 0; b < 2; ++b) {
+            const int gi = i0 + ty * 4 + a, gc = c0 + tx * 4 + 2 * b;
+            const float* xr = p.x_all + (size_t)(p.row0 + gi) * p.ld;
+            const float v0 = (gi < p.n_rows && gc < c_end) ? xr[gc] : 0.0f;
+            const float v1 = (gi < p.n_rows && gc + 1 < c_end) ? xr[gc + 1] : 0.0f;
+            xi[a][b] = pack2(v0, v1);
+            drive[a][b] = 0ull; rep[a][b] = 0ull;
         }
 
     for (int j0 = j_begin; j0 < j_end; j0 += PT_J) {
@@ -171,8 +175,10 @@ __global__ void __launch_bounds__(128) k_phi_partial(PairParams p) {
             int i = e / PT_J, j = e % PT_J;
             int gi = i0 + i, gj = j0 + j;
             bool ok = gi < p.n_rows && gj < j_end;
-            sK[j * PT_KP + i] = ok ? p.kfull[(size_t)gi * p.n_all + gj] : 0.0f;
-            sKt[j * PT_KP + i] = ok ? kterm[(size_t)gi * p.n_all + gj] : 0.0f;
+            const float kf = ok ? p.kfull[(size_t)gi * p.n_all + gj] : 0.0f;
+            const float kt = ok ? kterm[(size_t)gi * p.n_all + gj] : 0.0f;
+            *reinterpret_cast<float2*>(&sK[(j * PT_KP + i) * 2]) = make_float2(kf, kf);
+            *reinterpret_cast<float2*>(&sKt[(j * PT_KP + i) * 2]) = make_float2(kt, kt);
         }
         for (int e = tid; e < PT_J * (PT_C / 4); e += 128) {
             const int j = e / (PT_C / 4), c4 = (e % (PT_C / 4)) * 4;
@@ -198,19 +204,20 @@ __global__ void __launch_bounds__(128) k_phi_partial(PairParams p) {
         const int nj = min(PT_J, j_end - j0);
 #pragma unroll 4
         for (int j = 0; j < nj; ++j) {
-            const float4 kf4 = *reinterpret_cast<const float4*>(&sK[j * PT_KP + ty * 4]);
-            const float4 kt4 = *reinterpret_cast<const float4*>(&sKt[j * PT_KP + ty * 4]);
-            const float4 xj4 = *reinterpret_cast<const float4*>(&sXj[j * PT_C + tx * 4]);
-            const float4 gj4 = *reinterpret_cast<const float4*>(&sGj[j * PT_C + tx * 4]);
-            const float kf[4] = {kf4.x, kf4.y, kf4.z, kf4.w}, kt[4] = {kt4.x, kt4.y, kt4.z, kt4.w};
-            const float xj[4] = {xj4.x, xj4.y, xj4.z, xj4.w}, gj[4] = {gj4.x, gj4.y, gj4.z, gj4.w};
+            const ulonglong2 kfa = *reinterpret_cast<const ulonglong2*>(&sK[(j * PT_KP + ty * 4) * 2]);
+            const ulonglong2 kfb = *reinterpret_cast<const ulonglong2*>(&sK[(j * PT_KP + ty * 4 + 2) * 2]);
+            const ulonglong2 kta = *reinterpret_cast<const ulonglong2*>(&sKt[(j * PT_KP + ty * 4) * 2]);
+            const ulonglong2 ktb = *reinterpret_cast<const ulonglong2*>(&sKt[(j * PT_KP + ty * 4 + 2) * 2]);
+            const ulonglong2 xj = *reinterpret_cast<const ulonglong2*>(&sXj[j * PT_C + tx * 4]);
+            const ulonglong2 gj = *reinterpret_cast<const ulonglong2*>(&sGj[j * PT_C + tx * 4]);
+            const f32x2 kf[4] = {kfa.x, kfa.y, kfb.x, kfb.y}, kt[4] = {kta.x, kta.y, ktb.x, ktb.y};
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    drive[a][b] = fmaf(kf[a], gj[b], drive[a][b]);
-                    rep[a][b] = fmaf(kt[a], xj[b] - xi[a][b], rep[a][b]);
-                }
+            for (int a = 0; a < 4; ++a) {
+                drive[a][0] = fma2(kf[a], gj.x, drive[a][0]);
+                drive[a][1] = fma2(kf[a], gj.y, drive[a][1]);
+                rep[a][0] = fma2(kt[a], sub2(xj.x, xi[a][0]), rep[a][0]);
+                rep[a][1] = fma2(kt[a], sub2(xj.y, xi[a][1]), rep[a][1]);
+            }
         }
         __syncthreads();
     }
@@ -223,8 +230,8 @@ __global__ void __launch_bounds__(128) k_phi_partial(PairParams p) {
         const int gi = i0 + ty * 4 + a, gc = c0 + tx * 4;
         if (gi >= p.n_rows) continue;
         float* o = part + (size_t)gi * D + gc;
-        const float v0 = fmaf(c2, rep[a][0], drive[a][0]), v1 = fmaf(c2, rep[a][1], drive[a][1]);
-        const float v2 = fmaf(c2, rep[a][2], drive[a][2]), v3 = fmaf(c2, rep[a][3], drive[a][3]);
+        const float v0 = fmaf(c2, lo2(rep[a][0]), lo2(drive[a][0])), v1 = fmaf(c2, hi2(rep[a][0]), hi2(drive[a][0]));
+        const float v2 = fmaf(c2, lo2(rep[a][1]), lo2(drive[a][1])), v3 = fmaf(c2, hi2(rep[a][1]), hi2(drive[a][1]));
         if (gc + 3 < c_end && ((((size_t)blockIdx.z * p.n_rows + gi) * D + gc) & 3) == 0) {
             *reinterpret_cast<float4*>(o) = make_float4(v0, v1, v2, v3);
         } else {
@@ -237,8 +244,8 @@ __global__ void __launch_bounds__(128) k_phi_partial(PairParams p) {
 }
 
 // ---- pass 4: per particle, sum the j slices in fixed order -> phi, optimizer step, and -- because the whole new
-// latent row is in shared memory at that point -- the NEXT step's prologue: raw scores U V^T and per-pass sub-keys
-// (see k_prologue).  Block 0 also carries the loop state into the other StepState slot.
+// latent row is in shared memory at that point -- the NEXT step's raw scores U V^T (the edge-probability pass,
+// dibs.py:179-181; the next step's sub-keys and loop state come from k_assemble_grad).
 struct UpdateParams {
     const float* phi_part; int n_jsplit;      // [n_jsplit][n_rows][D]
     int n_rows, dz, dth, n_all;
@@ -247,11 +254,9 @@ struct UpdateParams {
     float* v; int v_ld;
     float* phi_out; int phi_ld;
     int optimizer; float stepsize;
-    const StepState* st_cur; StepState* st_next;
-    int n_step_splits, n_particles, partitionable;
-    // next-step prologue (scores null: skip)
-    int d, k, m_offset; uint32_t pre_split_mask;
-    float* scores; uint32_t* keys_out;
+    // next step's raw scores U V^T (null: skip)
+    int d, k;
+    float* scores;
 };
 
 __global__ void __launch_bounds__(256) k_opt_update(UpdateParams p) {
@@ -259,23 +264,6 @@ __global__ void __launch_bounds__(256) k_opt_update(UpdateParams p) {
     const int m = blockIdx.x, tid = threadIdx.x;
     const int D = p.dz + p.dth, d = p.d, k = p.k;
     float* sU = smem; float* sV = smem + k * d;       // new Z, de-interleaved and transposed: sU[kk][i], sV[kk][j]
-    // loop state: key <- after this step's (M+1)-way splits, t <- t + 1   (svgd.py:245,251,272)
-    if (p.st_cur && tid < 32) {
-        uint2 key = make_uint2(p.st_cur->key[0], p.st_cur->key[1]);
-        for (int w = 0; w < p.n_step_splits; ++w) key = jax_split_row(key, 0u, (uint32_t)p.n_particles + 1u, p.partitionable);
-        if (p.keys_out && tid < p.n_step_splits) {
-            uint2 sk = key;
-            for (int w = 0; w < tid; ++w) sk = jax_split_row(sk, 0u, (uint32_t)p.n_particles + 1u, p.partitionable != 0);
-            sk = jax_split_row(sk, (uint32_t)(p.m_offset + m) + 1u, (uint32_t)p.n_particles + 1u, p.partitionable != 0);
-            if ((p.pre_split_mask >> tid) & 1u) sk = jax_split_row(sk, 1u, 2u, p.partitionable != 0);
-            uint32_t* o = p.keys_out + ((size_t)tid * p.n_rows + m) * 2;
-            o[0] = sk.x; o[1] = sk.y;
-        }
-        if (m == 0 && tid == 0) {
-            p.st_next->key[0] = key.x; p.st_next->key[1] = key.y;
-            p.st_next->t = p.st_cur->t + 1; p.st_next->pad = 0;
-        }
-    }
     const float inv_m = 1.0f / (float)p.n_all;
     const size_t plane = (size_t)p.n_rows * D;
     const float* part = p.phi_part + (size_t)m * D;

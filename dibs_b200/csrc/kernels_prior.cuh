@@ -225,89 +225,138 @@ struct AsmParams {
     float sigma_z2;                       // latent_prior_std ** 2
     float* grad_z; int gz_ld;
     float* grad_th; int gth_ld;
+    // next step's loop state and per-pass sub-keys (step loop only; null: skip)
+    uint32_t* next_keys; StepState* st_next;
+    int n_step_splits, n_particles, partitionable, m_offset; uint32_t pre_split_mask;
 };
 
-__device__ __forceinline__ void merge_stats(const float* stats, int chunks, float& mx, float& l, float& sum_lp) {
-    mx = -INFINITY;
-    for (int c = 0; c < chunks; ++c) mx = fmaxf(mx, stats[c * 4]);
-    l = 0.0f; sum_lp = 0.0f;
-    for (int c = 0; c < chunks; ++c) {
-        float mc = stats[c * 4];
-        if (mc != -INFINITY) l += stats[c * 4 + 1] * expf(mc - mx);
-        sum_lp += stats[c * 4 + 2];
+// merged softmax normaliser of the chunk partials: weights w_c = exp(m_c - max) / sum_c l_c exp(m_c - max) into sW[c]
+// (one warp; chunks <= 32 handled by lanes, more by a strided loop), and sum of log-probs into *sum_lp
+__device__ __forceinline__ void merge_stats_warp(const float* __restrict__ stats, int chunks, float* sW, float* sum_lp,
+                                                 int lane) {
+    float mx = -INFINITY;
+    for (int c = lane; c < chunks; c += 32) mx = fmaxf(mx, stats[c * 4]);
+    mx = warp_max(mx);
+    float l = 0.0f, sl = 0.0f;
+    for (int c = lane; c < chunks; c += 32) {
+        const float mc = stats[c * 4];
+        const float w = (mc == -INFINITY) ? 0.0f : expf(mc - mx);
+        sW[c] = w;
+        l += stats[c * 4 + 1] * w;
+        sl += stats[c * 4 + 2];
     }
+    // fixed-order (butterfly) sums: deterministic
+    l = warp_sum(l); sl = warp_sum(sl);
+    __syncwarp();
+    for (int c = lane; c < chunks; c += 32) sW[c] = sW[c] / l;
+    if (lane == 0) *sum_lp = sl;
 }
 
+// Latency-bound by construction (one CTA per particle, a few KB of inputs): every global read is issued as early as
+// possible and branch-free so the loads of a phase overlap; the serial threefry chains of the NEXT step's sub-keys
+// run on an otherwise idle warp underneath.
 __global__ void __launch_bounds__(256) k_assemble_grad(AsmParams p) {
     extern __shared__ __align__(16) float smem[];
-    const int d = p.d, k = p.k, tid = threadIdx.x, m = blockIdx.x;
+    const int d = p.d, k = p.k, dd = d * d, tid = threadIdx.x, m = blockIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t = p.st ? p.st->t : p.t_override;
     const float alpha = p.alpha_linear * (float)t;
     const float beta = p.beta_linear * (float)t;
     float* sZ = smem;                 // [2dk]
     float* sP = sZ + 2 * d * k;       // [d*d]
-    float* sDS = sP + d * d;          // [d*d]
-    float* sCol = sDS + d * d;        // [d]
+    float* sDS = sP + dd;             // [d*d]
+    float* sCol = sDS + dd;           // [d]
+    float* sWz = sCol + d;            // [z_chunks]
+    float* sWt = sWz + p.z_chunks;    // [th_chunks]
+    float* sMisc = sWt + p.th_chunks; // [2] sum of z log-probs, sum of theta log-probs
 
+    // ---- phase A: stage Z and the edge probabilities; warp 0/1 merge the softmax statistics; warp 7 derives keys
     const float* zrow = p.z + (size_t)m * p.z_ld;
     for (int e = tid; e < 2 * d * k; e += blockDim.x) sZ[e] = zrow[e];
-    __syncthreads();
-    for (int e = tid; e < d * d; e += blockDim.x) {
-        int i = e / d, j = e % d;
-        sP[e] = (i == j) ? 0.0f : sigmoidf_ref(alpha * p.scores[(size_t)m * d * d + e]);
+    for (int e = tid; e < dd; e += blockDim.x) {
+        const int i = e / d, j = e - i * d;
+        sP[e] = (i == j) ? 0.0f : sigmoidf_ref(alpha * p.scores[(size_t)m * dd + e]);
+    }
+    if (warp == 0 && p.zacc) merge_stats_warp(p.zstats + (size_t)m * p.z_chunks * 4, p.z_chunks, sWz, sMisc, lane);
+    if (warp == 1 && p.thacc) merge_stats_warp(p.thstats + (size_t)m * p.th_chunks * 4, p.th_chunks, sWt, sMisc + 1, lane);
+    if (warp == 7 && p.next_keys) {
+        // loop state: key <- after this step's (M+1)-way splits, t <- t + 1 (svgd.py:245,251,272); the sub-keys of
+        // the next step (svgd.py:245,251 / 695,699,703 and the pre-draw splits dibs.py:350,430) for this particle
+        uint2 key = make_uint2(p.st->key[0], p.st->key[1]);
+        for (int w = 0; w < p.n_step_splits; ++w) key = jax_split_row(key, 0u, (uint32_t)p.n_particles + 1u, p.partitionable != 0);
+        if (lane < p.n_step_splits) {
+            uint2 sk = key;
+            for (int w = 0; w < lane; ++w) sk = jax_split_row(sk, 0u, (uint32_t)p.n_particles + 1u, p.partitionable != 0);
+            sk = jax_split_row(sk, (uint32_t)(p.m_offset + m) + 1u, (uint32_t)p.n_particles + 1u, p.partitionable != 0);
+            if ((p.pre_split_mask >> lane) & 1u) sk = jax_split_row(sk, 1u, 2u, p.partitionable != 0);
+            uint32_t* o = p.next_keys + ((size_t)lane * p.n_local + m) * 2;
+            o[0] = sk.x; o[1] = sk.y;
+        }
+        if (m == 0 && lane == 0) {
+            p.st_next->key[0] = key.x; p.st_next->key[1] = key.y;
+            p.st_next->t = t + 1; p.st_next->pad = 0;
+        }
     }
     __syncthreads();
-    if (p.acyc && !p.constraint_only && p.prior_kind == 1 && tid < d) {
-        float indeg = 0.0f;
-        for (int i = 0; i < d; ++i) indeg += sP[i * d + tid];        // soft_g.sum(0)  (graph.py:195)
-        sCol[tid] = -3.0f / (1.0f + indeg);
+    if (p.acyc && !p.constraint_only && p.prior_kind == 1) {
+        if (tid < d) {
+            float indeg = 0.0f;
+            for (int i = 0; i < d; ++i) indeg += sP[i * d + tid];        // soft_g.sum(0)  (graph.py:195)
+            sCol[tid] = -3.0f / (1.0f + indeg);
+        }
+        __syncthreads();
     }
-    // likelihood partial merge (uniform per CTA)
-    float zmx = 0.0f, zl = 1.0f, zsum = 0.0f, base_fac = 1.0f;
-    if (p.zacc) {
-        merge_stats(p.zstats + (size_t)m * p.z_chunks * 4, p.z_chunks, zmx, zl, zsum);
-        if (p.z_mode == MC_Z_SCORE && p.sf_coef > 0.0f) base_fac = expf(-p.baselines_in[m]);
-    }
-    __syncthreads();
-    for (int e = tid; e < d * d; e += blockDim.x) {
-        int i = e / d, j = e % d;
+    const float base_fac = (p.zacc && p.z_mode == MC_Z_SCORE && p.sf_coef > 0.0f) ? expf(-p.baselines_in[m]) : 1.0f;
+    // ---- phase B: dS
+    const float inv_acyc = 1.0f / (float)p.n_acyc;
+    for (int e = tid; e < dd; e += blockDim.x) {
+        const int i = e / d, j = e - i * d;
+        float w = 0.0f, acs = 0.0f;
+        if (p.zacc) {
+            const float* za = p.zacc + (size_t)m * p.z_chunks * dd + e;
+            for (int c = 0; c < p.z_chunks; ++c) w = fmaf(za[(size_t)c * dd], sWz[c], w);
+        }
+        if (p.acyc) {
+            const float* ac = p.acyc + (size_t)m * p.acyc_chunks * dd + e;
+            for (int c = 0; c < p.acyc_chunks; ++c) acs += ac[(size_t)c * dd];
+        }
         float ds = 0.0f;
         if (i != j) {
-            float pe = sP[e];
-            if (p.zacc) {
-                float num = 0.0f;
-                for (int c = 0; c < p.z_chunks; ++c) {
-                    float mc = p.zstats[((size_t)m * p.z_chunks + c) * 4];
-                    if (mc != -INFINITY) num += p.zacc[((size_t)m * p.z_chunks + c) * d * d + e] * expf(mc - zmx);
-                }
-                float w = num / zl;
-                // score: e^{-b} alpha (Gbar - P) (App. B-1/2; dibs.py:363-382); reparam: softmax-weighted dS
-                ds += (p.z_mode == MC_Z_SCORE) ? base_fac * alpha * (w - pe) : w;
-            }
+            const float pe = sP[e];
+            // score: e^{-b} alpha (Gbar - P) (App. B-1/2; dibs.py:363-382); reparam: softmax-weighted dS
+            if (p.zacc) ds += (p.z_mode == MC_Z_SCORE) ? base_fac * alpha * (w - pe) : w;
             if (p.acyc) {
-                float acs = 0.0f;
-                for (int c = 0; c < p.acyc_chunks; ++c) acs += p.acyc[((size_t)m * p.acyc_chunks + c) * d * d + e];
-                float ac = acs / (float)p.n_acyc;    // .mean(0)  (dibs.py:601)
-                if (p.constraint_only) ds += ac;
+                const float acm = acs * inv_acyc;                                  // .mean(0)  (dibs.py:601)
+                if (p.constraint_only) ds += acm;
                 else {
-                    ds -= beta * ac;
-                    float coef = p.prior_kind == 0 ? p.er_coef : (p.prior_kind == 1 ? sCol[j] : 0.0f);
-                    ds += coef * alpha * pe * (1.0f - pe);                      // App. B-5
+                    ds -= beta * acm;
+                    const float coef = p.prior_kind == 0 ? p.er_coef : (p.prior_kind == 1 ? sCol[j] : 0.0f);
+                    ds += coef * alpha * pe * (1.0f - pe);                          // App. B-5
                 }
             }
         }
         sDS[e] = ds;
     }
+    // theta gradient: softmax-weighted partial sums (dibs.py:531-549); independent of the barrier below
+    if (p.thacc) {
+        float* gth = p.grad_th + (size_t)m * p.gth_ld;
+        const float* ta = p.thacc + (size_t)m * p.th_chunks * p.th_dim;
+        for (int e = tid; e < p.th_dim; e += blockDim.x) {
+            float num = 0.0f;
+            for (int c = 0; c < p.th_chunks; ++c) num = fmaf(ta[(size_t)c * p.th_dim + e], sWt[c], num);
+            gth[e] = num;
+        }
+    }
     __syncthreads();
-    // chain rule through S = U V^T: dU = dS V, dV = dS^T U; Gaussian prior -Z/sigma^2 (dibs.py:657)
+    // ---- phase C: chain rule through S = U V^T: dU = dS V, dV = dS^T U; Gaussian prior -Z/sigma^2 (dibs.py:657)
     float* gz = p.grad_z + (size_t)m * p.gz_ld;
     const bool gauss = p.acyc && !p.constraint_only;
     for (int e = tid; e < d * k; e += blockDim.x) {
-        int i = e / k, kk = e % k;
+        const int i = e / k, kk = e - i * k;
         float du = 0.0f, dv = 0.0f;
         for (int j = 0; j < d; ++j) {
-            du = fmaf(sDS[i * d + j], sZ[(j * k + kk) * 2 + 1], du);
-            dv = fmaf(sDS[j * d + i], sZ[(j * k + kk) * 2], dv);
+            const float2 zj = *reinterpret_cast<const float2*>(&sZ[(j * k + kk) * 2]);
+            du = fmaf(sDS[i * d + j], zj.y, du);
+            dv = fmaf(sDS[j * d + i], zj.x, dv);
         }
         if (gauss) {
             du -= sZ[2 * e] / p.sigma_z2;
@@ -316,27 +365,17 @@ __global__ void __launch_bounds__(256) k_assemble_grad(AsmParams p) {
         gz[2 * e] = du; gz[2 * e + 1] = dv;
     }
     if (p.zacc && p.baselines_out && tid == 0) {
-        float b_in = p.baselines_in ? p.baselines_in[m] : 0.0f;
+        const float b_in = p.baselines_in ? p.baselines_in[m] : 0.0f;
         // dibs.py:388-389 (only the score estimator touches the baseline)
         p.baselines_out[m] = (p.z_mode == MC_Z_SCORE)
-            ? p.sf_coef * (zsum / (float)p.n_samples) + (1.0f - p.sf_coef) * b_in : b_in;
-    }
-    if (p.thacc) {
-        float tmx, tl, tsum;
-        merge_stats(p.thstats + (size_t)m * p.th_chunks * 4, p.th_chunks, tmx, tl, tsum);
-        float* gth = p.grad_th + (size_t)m * p.gth_ld;
-        for (int e = tid; e < p.th_dim; e += blockDim.x) {
-            float num = 0.0f;
-            for (int c = 0; c < p.th_chunks; ++c) {
-                float mc = p.thstats[((size_t)m * p.th_chunks + c) * 4];
-                if (mc != -INFINITY) num += p.thacc[((size_t)m * p.th_chunks + c) * p.th_dim + e] * expf(mc - tmx);
-            }
-            gth[e] = num / tl;
-        }
+            ? p.sf_coef * (sMisc[0] / (float)p.n_samples) + (1.0f - p.sf_coef) * b_in : b_in;
     }
 }
 
-inline size_t assemble_smem(int d, int k) { return ((size_t)2 * d * k + 2 * (size_t)d * d + d) * sizeof(float); }
+inline size_t assemble_smem(int d, int k, int z_chunks, int th_chunks) {
+    return ((size_t)2 * d * k + 2 * (size_t)d * d + d + z_chunks + th_chunks + 4) * sizeof(float);
+}
+
 
 // edge_probs / particle_to_g_lim hooks (dibs.py:84-99,168-184); one CTA per particle
 __global__ void __launch_bounds__(256) k_edge_probs(const float* z, int z_ld, int d, int k, float alpha,
