@@ -19,6 +19,7 @@
 #include "kernels_mc_nn.cuh"
 #include "kernels_prior.cuh"
 #include "kernels_acyclic.cuh"
+#include "kernels_dense.cuh"
 #include "kernels_pair.cuh"
 #include "kernels_init.cuh"
 
@@ -125,6 +126,9 @@ struct dibs_plan {
     // LinearGaussian, observational data, d <= 32: packed upper-triangular QR factor of x (kernels_mc_lin_qr.cuh)
     bool use_qr = false;
     std::vector<float> lin_r;
+    // LinearGaussian, observational data, n_vars > 32: dense Rx and Rx^T on the device (kernels_dense.cuh)
+    bool use_dense = false;
+    float* rx_dense = nullptr;
     // MC workspace
     int max_chunks = 1, th_acc_size = 0;
     float *th_acc = nullptr, *th_stats = nullptr, *z_acc = nullptr, *z_stats = nullptr, *acyc = nullptr;
@@ -180,6 +184,7 @@ static bool acyc_rows_path(const dibs_plan* p) {
     return p->d <= 32 && (p->cfg.n_acyclicity_mc_samples % 2) == 0 && !p->cfg.prng_partitionable && !getenv("DIBS_B200_OLD_ACYCLIC");
 }
 static int acyc_chunks(const dibs_plan* p) {
+    if (p->d > 32) return acyc_dense_shape(p->d, p->cfg.n_acyclicity_mc_samples).chunks;
     return acyc_rows_path(p) ? ceil_div(p->cfg.n_acyclicity_mc_samples / 2, ACYC_WPC) : 1;
 }
 
@@ -192,7 +197,8 @@ struct McShape {
     int chunks;     // CTAs per particle (blockIdx.y)
     int spc;        // samples (or slots) per chunk
     int threads;    // CTA size
-    bool paired;    // BGe: a slot is the sample pair (s, s + S/2)
+    bool paired;    // a slot is the sample pair (s, s + S/2)
+    bool dense;     // LinearGaussian n_vars > 32: whole-graph matrix-product kernel, units are samples
 };
 
 static bool qr_eligible(int likelihood, int dmax) { return likelihood == DIBS_LIK_LINEAR_GAUSSIAN && dmax <= 32; }
@@ -201,6 +207,7 @@ static McShape mc_shape_for(bool qr, int likelihood, int d, int hidden, int n_lo
     McShape sh;
     sh.qr = qr;
     sh.paired = false;
+    sh.dense = false;
     if (n_local < 1) n_local = 1;
     if (qr) {
         const int Q = (S + 1) / 2;
@@ -243,6 +250,20 @@ static McShape mc_shape_for(bool qr, int likelihood, int d, int hidden, int n_lo
     if (want > max_chunks) want = max_chunks;
     sh.spc = ceil_div(ceil_div(S, want), gpb) * gpb;
     sh.chunks = ceil_div(S, sh.spc);
+    return sh;
+}
+
+static McShape mc_shape_dense(int d, int n_local, int S) {
+    McShape sh;
+    sh.qr = false; sh.paired = false; sh.dense = true;
+    if (n_local < 1) n_local = 1;
+    int want = ceil_div(4 * 148, n_local);
+    if (want > S) want = S;
+    if (want < 1) want = 1;
+    sh.spc = ceil_div(S, want);
+    sh.chunks = ceil_div(S, sh.spc);
+    sh.gpb = 1;
+    sh.threads = ((dense_nt(d) + 31) / 32) * 32;
     return sh;
 }
 
@@ -299,6 +320,10 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
         {
             McShape b = mc_shape_for(false, c.likelihood, d, c.hidden, p->M_loc, S, true);
             if (b.chunks > p->max_chunks) p->max_chunks = b.chunks;
+            if (c.likelihood == DIBS_LIK_LINEAR_GAUSSIAN && d > 32) {
+                b = mc_shape_dense(d, p->M_loc, S);
+                if (b.chunks > p->max_chunks) p->max_chunks = b.chunks;
+            }
         }
 
         if (qr_eligible(c.likelihood, p->dmax)) {
@@ -380,7 +405,7 @@ extern "C" int dibs_plan_destroy(dibs_plan* p) {
     if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
     for (int i = 0; i < 3; ++i) { if (p->aux[i]) cudaStreamDestroy(p->aux[i]); if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]); }
     for (int i = 0; i < 2; ++i) if (p->ev_fork[i]) cudaEventDestroy(p->ev_fork[i]);
-    void* ptrs[] = {p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->v, p->base, p->st, p->step_keys, p->scores,
+    void* ptrs[] = {p->rx_dense, p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->v, p->base, p->st, p->step_keys, p->scores,
                     p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->dist_part, p->kz, p->kt, p->kfull, p->phi_part};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
@@ -448,6 +473,27 @@ extern "C" int dibs_set_data(dibs_plan* p, const float* x, const int32_t* mask, 
         qr_upper_packed(hx, n_obs, d, p->dmax, p->lin_r);
         p->use_qr = true;
     }
+    p->use_dense = false;
+    if (p->cfg.likelihood == DIBS_LIK_LINEAR_GAUSSIAN && d > 32 && !p->has_mask && lin_dense_smem(d) <= 227 * 1024 &&
+        !getenv("DIBS_B200_NO_QR")) {
+        std::vector<float> hx((size_t)n_obs * d), packed;
+        CU(cudaMemcpyAsync(hx.data(), p->x, hx.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        qr_upper_packed(hx, n_obs, d, d, packed);      // packed with stride d: row i starts at i*d - i(i-1)/2
+        const int ld = dense_ld(d);
+        std::vector<float> dense((size_t)2 * ld * ld, 0.0f);
+        for (int i = 0; i < d; ++i)
+            for (int k = i; k < d; ++k) {
+                const float v = packed[(size_t)i * d - (size_t)i * (i - 1) / 2 + (k - i)];
+                dense[(size_t)i * ld + k] = v;                          // Rx[i][k]
+                dense[(size_t)ld * ld + (size_t)k * ld + i] = v;        // Rx^T[k][i]
+            }
+        if (p->rx_dense) { cudaFree(p->rx_dense); p->rx_dense = nullptr; }
+        CU(cudaMalloc((void**)&p->rx_dense, dense.size() * sizeof(float)));
+        CU(cudaMemcpyAsync(p->rx_dense, dense.data(), dense.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));
+        p->use_dense = true;
+    }
     if (p->cfg.likelihood == DIBS_LIK_BGE) TRY(bge_prepare(p->cfg, d, n_obs, p->x, p->mask, bge_mean_obs_host, &p->bge_r,
                                                        &p->bge_table, &p->bge_coef, &p->bge_r_stride, stream, g_last_error));
     p->has_data = true;
@@ -460,6 +506,7 @@ extern "C" int dibs_set_data(dibs_plan* p, const float* x, const int32_t* mask, 
 // pass shape for this plan: the QR kernel needs observational data and -- unless the graphs are supplied by the
 // caller (lp_only hook) -- the legacy threefry layout with an even number of samples (two draws per block)
 static McShape mc_shape(const dibs_plan* p, int n_local, int S, bool lp_only) {
+    if (p->use_dense) return mc_shape_dense(p->d, n_local, S);
     const bool qr = p->use_qr && (lp_only || (!p->cfg.prng_partitionable && (S % 2) == 0));
     return mc_shape_for(qr, p->cfg.likelihood, p->d, p->cfg.hidden, n_local, S, !lp_only && !p->cfg.prng_partitionable);
 }
@@ -526,6 +573,14 @@ static int launch_mc(const dibs_plan* p, McParams q, const McShape& sh, cudaStre
     const int lik = p->cfg.likelihood;
     size_t smem = 0;
     int e = 0;
+    if (sh.dense) {
+        smem = lin_dense_smem(p->d);
+        auto kern = k_mc_lin_dense<MODE>;
+        TRY(set_smem(kern, smem));
+        kern<<<grid, sh.threads, smem, stream>>>(q, p->rx_dense, dense_ld(p->d), dense_nt(p->d));
+        LAUNCHED();
+        return DIBS_OK;
+    }
     if (sh.qr) {
         smem = mc_lin_qr_smem(p->dmax, q.gpb);
         if (smem > 227 * 1024) return fail(DIBS_ERR_UNSUPPORTED, "problem size needs more than 227 KB of shared memory per CTA");
@@ -593,9 +648,10 @@ static int launch_acyc(const dibs_plan* p, const Src& s, int which_split, float*
         TRY(set_smem(k_acyclic_grad<true>, smem));
         k_acyclic_grad<true><<<s.n, warps * 32, smem, stream>>>(a);
     } else {
-        size_t smem = acyclic_smem(d, p->k, 1);
-        TRY(set_smem(k_acyclic_grad<false>, smem));
-        k_acyclic_grad<false><<<s.n, 256, smem, stream>>>(a);
+        // register-tiled matrix powers on shared-memory operands (kernels_dense.cuh)
+        const AcycDenseShape sh = acyc_dense_shape(d, a.n_samples);
+        TRY(set_smem(k_acyclic_dense, sh.smem));
+        k_acyclic_dense<<<dim3(s.n, sh.chunks), sh.threads, sh.smem, stream>>>(a, sh.ld, sh.nt, sh.ng, sh.rounds);
     }
     LAUNCHED();
     return DIBS_OK;

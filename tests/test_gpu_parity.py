@@ -221,15 +221,15 @@ def _mid_case(lik, d=20, m=8, s=32, a=8, n_obs=100, hidden=5, seed=0):
     return g
 
 
-@pytest.mark.parametrize("lik", ["lingauss", "densenn", "bge"])
-def test_step_vs_oracle_n_vars_20(lik):
-    """BASELINE-shaped problem (n_vars=20, N=100) at a particle count the oracle finishes in seconds:
-    values vs the fp32 oracle at 1e-5, estimators bounded by the fp32-vs-fp64 oracle gap."""
+@pytest.mark.parametrize("lik,d,m,s", [("lingauss", 20, 8, 32), ("densenn", 20, 8, 32), ("bge", 20, 8, 32),
+                                       ("lingauss", 50, 4, 8), ("lingauss", 40, 3, 6), ("bge", 40, 4, 8)])
+def test_step_vs_oracle_n_vars_20(lik, d, m, s):
+    """BASELINE-shaped problems (n_vars=20, N=100; n_vars=40/50 for the n_vars > 32 kernels) at a particle count the
+    oracle finishes in seconds: values vs the fp32 oracle at 1e-5, estimators bounded by the fp32-vs-fp64 oracle gap."""
     from dibs_b200.inference import PRNGKey
-    g = _mid_case(lik)
+    g = _mid_case(lik, d=d, m=m, s=s)
     model = build_model(g, sample_case=True)
     cfg = oracle_config(g, sample_case=True)
-    m, d = 8, 20
     key = PRNGKey(3)
     st32 = orc.init_particles(cfg, key, m, None, np.float32)
     st32.z = (st32.z * 2.0).astype(np.float32)
