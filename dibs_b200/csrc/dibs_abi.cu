@@ -227,6 +227,23 @@ static McShape mc_shape_for(bool qr, int likelihood, int d, int hidden, int n_lo
         sh.spc = rpc * best;
         return sh;
     }
+    if (likelihood == DIBS_LIK_BGE) {
+        // whole chunk of slots (sample pairs when the PRNG layout allows) per CTA, as many as shared memory holds
+        sh.paired = pair_ok && (S % 2) == 0;
+        const int per = sh.paired ? 2 : 1;
+        const int Q = sh.paired ? S / 2 : S;
+        int want = ceil_div(2 * 148, n_local);
+        if (want > Q) want = Q;
+        if (want < 1) want = 1;
+        int spc = ceil_div(Q, want);
+        const int dmax = d <= 8 ? 8 : d <= 16 ? 16 : d <= 20 ? 20 : d <= 32 ? 32 : 64;
+        while (spc > 1 && (spc * per > 256 || mc_bge_smem(d, dmax, spc * per, true) > 200 * 1024)) spc = (spc + 1) / 2;
+        sh.spc = spc;
+        sh.chunks = ceil_div(Q, spc);
+        sh.gpb = spc;
+        sh.threads = 256;
+        return sh;
+    }
     if (likelihood == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN) {
         // one slot (sample pair when the PRNG layout allows, else one sample) at a time per CTA; chunks of slots
         sh.paired = pair_ok && (S % 2) == 0;
@@ -600,7 +617,7 @@ static int launch_mc(const dibs_plan* p, McParams q, const McShape& sh, cudaStre
         smem = mc_nn_smem(p->d, p->N, p->dmax, q.hidden, q.mask != nullptr);
     } else {
         if (MODE != MC_Z_SCORE && MODE != MC_LP_ONLY) return fail(DIBS_ERR_UNSUPPORTED, "BGe supports the score estimator only");
-        smem = mc_bge_smem(p->d, p->k, q.gpb);
+        smem = mc_bge_smem(p->d, p->dmax, q.s_per_chunk * (q.paired ? 2 : 1), p->bge_r_stride == 0);
     }
     if (smem > 227 * 1024) return fail(DIBS_ERR_UNSUPPORTED, "problem size needs more than 227 KB of shared memory per CTA");
 #define GO(FAM) switch (p->dmax) { case 8: e = launch_mc_##FAM##_8(MODE, q, grid, smem, stream); break; \
