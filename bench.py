@@ -107,9 +107,11 @@ def kernel_work(name, m_loc, m_all):
     w["allgather"] = dict(flops=0, bytes=(m_all - m_loc) * 4 * 2 * dd, bound="nvlink")
     w["pair_dist"] = dict(flops=3 * m_loc * m_all * dd, bytes=4 * (m_all * dd + m_loc * m_all), bound="fp32")
     w["pair_kernel"] = dict(flops=4 * m_loc * m_all, bytes=4 * m_loc * m_all * (3 if dth else 2), bound="hbm")
-    w["step_keys"] = dict(flops=0, bytes=m_loc * 8 * (3 if lik != "bge" else 2), bound="latency")
-    w["phi_update"] = dict(flops=2 * 2 * m_loc * m_all * dd, bytes=4 * (2 * m_all * dd + 4 * m_loc * dd + 2 * m_loc * m_all),
+    # phi: per-slice partial sums (the optimizer, the state traffic and the NEXT step's edge-probability pass -- raw
+    # scores U V^T -- are the per-particle k_opt_update kernel)
+    w["phi_update"] = dict(flops=2 * 2 * m_loc * m_all * dd, bytes=4 * (2 * m_all * dd + 2 * m_loc * dd + 2 * m_loc * m_all),
                            bound="fp32")
+    w["opt_update"] = dict(flops=m_loc * (edge + 8 * dd), bytes=m_loc * 4 * (6 * dd + d * d), bound="hbm")
     return w
 
 

@@ -57,7 +57,7 @@ PROTOTYPES = {
     "dibs_launch_count": (ctypes.c_int64, []),
 }
 
-PHASES = ("mc_theta", "mc_z", "acyclic", "assemble", "allgather", "pair_dist", "pair_kernel", "phi_update", "step_keys")
+PHASES = ("mc_theta", "mc_z", "acyclic", "assemble", "allgather", "pair_dist", "pair_kernel", "phi_update", "opt_update")
 
 _lib = None
 

@@ -184,6 +184,7 @@ static bool acyc_rows_path(const dibs_plan* p) {
     return p->d <= 32 && (p->cfg.n_acyclicity_mc_samples % 2) == 0 && !p->cfg.prng_partitionable && !getenv("DIBS_B200_OLD_ACYCLIC");
 }
 static int acyc_chunks(const dibs_plan* p) {
+    if (p->d > 32 && p->d <= 64) return acyc_dense4_shape(p->d, p->cfg.n_acyclicity_mc_samples).chunks;
     if (p->d > 32) return acyc_dense_shape(p->d, p->cfg.n_acyclicity_mc_samples).chunks;
     return acyc_rows_path(p) ? ceil_div(p->cfg.n_acyclicity_mc_samples / 2, ACYC_WPC) : 1;
 }
@@ -664,6 +665,11 @@ static int launch_acyc(const dibs_plan* p, const Src& s, int which_split, float*
         while (smem > 200 * 1024 && warps > 1) { warps /= 2; smem = acyclic_smem(d, p->k, warps); }
         TRY(set_smem(k_acyclic_grad<true>, smem));
         k_acyclic_grad<true><<<s.n, warps * 32, smem, stream>>>(a);
+    } else if (d <= 64) {
+        // 4 x 4 register tiles: one sample per CTA at a time, several CTAs per SM
+        const AcycDenseShape sh = acyc_dense4_shape(d, a.n_samples);
+        TRY(set_smem(k_acyclic_dense4, sh.smem));
+        k_acyclic_dense4<<<dim3(s.n, sh.chunks), sh.threads, sh.smem, stream>>>(a, sh.ld, sh.nt, sh.rounds);
     } else {
         // register-tiled matrix powers on shared-memory operands (kernels_dense.cuh)
         const AcycDenseShape sh = acyc_dense_shape(d, a.n_samples);

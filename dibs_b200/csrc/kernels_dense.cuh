@@ -216,6 +216,163 @@ __global__ void __launch_bounds__(256, 1) k_acyclic_dense(AcycParams p, int LD, 
 }
 
 // ------------------------------------------------------------------------------------------
+// same pass with 4 x 4 register tiles (rows 4ty.., columns 4tx.., LD multiple of 4): four times the threads per
+// matrix and a quarter of the shared memory per thread -- the better trade for 32 < n_vars <= 64, where an 8 x 8
+// tiling leaves a CTA with < 64 threads per sample
+// ------------------------------------------------------------------------------------------
+struct Tile4 { f32x2 c[4][2]; };
+
+__device__ __forceinline__ void tile4_mm(const float* __restrict__ At, const float* __restrict__ B, int LD, int ty, int tx,
+                                         int k0, int k1, Tile4& t) {
+    const float* ap = At + (size_t)k0 * LD + 4 * ty;
+    const float* bp = B + (size_t)k0 * LD + 4 * tx;
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k, ap += LD, bp += LD) {
+        const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(bp);
+        const float4 a = *reinterpret_cast<const float4*>(ap);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const f32x2 aa = pack2(av[r], av[r]);
+            t.c[r][0] = fma2(aa, b.x, t.c[r][0]);
+            t.c[r][1] = fma2(aa, b.y, t.c[r][1]);
+        }
+    }
+}
+__device__ __forceinline__ float tile4_get(const Tile4& t, int a, int b) { return (b & 1) ? hi2(t.c[a][b >> 1]) : lo2(t.c[a][b >> 1]); }
+__device__ __forceinline__ void tile4_store(const Tile4& t, float* M, int LD, int ty, int tx) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+        *reinterpret_cast<ulonglong2*>(M + (size_t)(4 * ty + a) * LD + 4 * tx) = make_ulonglong2(t.c[a][0], t.c[a][1]);
+}
+__device__ __forceinline__ void tile4_store_t(const Tile4& t, float* Mt, int LD, int ty, int tx) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+        *reinterpret_cast<float4*>(Mt + (size_t)(4 * tx + b) * LD + 4 * ty) =
+            make_float4(tile4_get(t, 0, b), tile4_get(t, 1, b), tile4_get(t, 2, b), tile4_get(t, 3, b));
+}
+
+static inline AcycDenseShape acyc_dense4_shape(int d, int n_samples) {
+    AcycDenseShape s;
+    s.ld = (d + 3) & ~3;
+    const int q = s.ld / 4;
+    s.nt = q * q;
+    const size_t mat = (size_t)s.ld * s.ld * sizeof(float);
+    s.ng = 1;
+    s.threads = ((s.nt + 31) / 32) * 32;
+    s.rounds = (n_samples + 7) / 8;                      // <= 8 chunks per particle, fixed decomposition
+    s.chunks = (n_samples + s.rounds - 1) / s.rounds;
+    s.smem = 4 * mat + (size_t)d * d * sizeof(float) + 64;
+    return s;
+}
+
+__global__ void __launch_bounds__(256, 2) k_acyclic_dense4(AcycParams p, int LD, int NT, int rounds) {
+    extern __shared__ __align__(16) float smem[];
+    const int d = p.d, dd = d * d, TQ = LD / 4;
+    const int m = blockIdx.x, tid = threadIdx.x;
+    const int t = p.st ? p.st->t : p.t_override;
+    const float alpha = p.alpha_linear * (float)t;
+    const int MAT = LD * LD;
+    const bool active = tid < NT;
+    const int ty = active ? tid / TQ : 0, tx = active ? tid - ty * TQ : 0;
+
+    float* sS = smem;                                   // [dd] alpha*scores, or exp(-alpha*scores) when tau == 1
+    float* sG = smem + ((dd + 3) & ~3);                 // soft graph
+    float* sZ = sG + MAT;                               // running square (row-major)
+    float* sZt = sZ + MAT;                              // its transpose
+    float* sRt = sZt + MAT;                             // running result, transposed
+
+    const bool fast_soft = p.tau == 1.0f;
+    for (int e = tid; e < dd; e += blockDim.x) {
+        const float a = alpha * p.scores[(size_t)m * dd + e];
+        sS[e] = fast_soft ? expf(-a) : a;
+    }
+    for (int e = tid; e < 4 * MAT; e += blockDim.x) sG[e] = 0.0f;          // padding stays zero
+    const uint2 key = make_uint2(p.keys_override[2 * m], p.keys_override[2 * m + 1]);
+    __syncthreads();
+
+    const float inv_d = 1.0f / (float)d;
+    const float ta = p.tau * alpha;
+    const uint32_t n_total = (uint32_t)p.n_samples * dd;
+    Tile4 acc;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { acc.c[a][0] = 0ull; acc.c[a][1] = 0ull; }
+
+    for (int r = 0; r < rounds; ++r) {
+        const int a = blockIdx.y * rounds + r;
+        if (a >= p.n_samples) break;                    // CTA-uniform
+        for (int i = tid / d, j = tid - (tid / d) * d, e = tid; e < dd; e += blockDim.x) {
+            float g = 0.0f;
+            if (i != j) {
+                const uint32_t bits = jax_bits(key, (uint32_t)a * dd + e, n_total, p.partitionable);
+                g = entry_from_bits<false>(bits, sS[e], fast_soft, p.tau);
+            }
+            const float mz = (i == j ? 1.0f : 0.0f) + inv_d * g;            // graph_utils.py:22-25
+            sG[i * LD + j] = g; sZ[i * LD + j] = mz; sZt[j * LD + i] = mz;
+            j += blockDim.x;
+            while (j >= d) { j -= d; ++i; }
+        }
+        __syncthreads();
+        // E = M^(d-1): binary exponentiation, least-significant bit first (jnp.linalg.matrix_power)
+        bool have_res = false;
+        int n = d - 1;
+        while (n > 0) {
+            if (n & 1) {
+                if (!have_res) {
+                    for (int e = tid; e < MAT; e += blockDim.x) sRt[e] = sZt[e];
+                    have_res = true;
+                    __syncthreads();
+                } else {
+                    Tile4 c;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { c.c[q][0] = 0ull; c.c[q][1] = 0ull; }
+                    if (active) tile4_mm(sRt, sZ, LD, ty, tx, 0, d, c);      // res * Z
+                    __syncthreads();
+                    if (active) tile4_store_t(c, sRt, LD, ty, tx);
+                    __syncthreads();
+                }
+            }
+            n >>= 1;
+            if (n > 0) {
+                Tile4 c;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { c.c[q][0] = 0ull; c.c[q][1] = 0ull; }
+                if (active) tile4_mm(sZt, sZ, LD, ty, tx, 0, d, c);          // Z * Z
+                __syncthreads();
+                if (active) { tile4_store(c, sZ, LD, ty, tx); tile4_store_t(c, sZt, LD, ty, tx); }
+                __syncthreads();
+            }
+        }
+        // dS[a][b] = E[b][a] * tau alpha g_ab (1 - g_ab) = Rt[a][b] * F[a][b]
+        if (active) {
+#pragma unroll
+            for (int a4 = 0; a4 < 4; ++a4) {
+                const int row = 4 * ty + a4;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int col = 4 * tx + 2 * q;
+                    const float2 g = *reinterpret_cast<const float2*>(&sG[row * LD + col]);
+                    const float2 e = *reinterpret_cast<const float2*>(&sRt[row * LD + col]);
+                    const f32x2 f = pack2(ta * g.x * (1.0f - g.x), ta * g.y * (1.0f - g.y));
+                    acc.c[a4][q] = fma2(pack2(e.x, e.y), f, acc.c[a4][q]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    float* outp = p.ds_out + ((size_t)m * gridDim.y + blockIdx.y) * dd;
+    if (active) {
+#pragma unroll
+        for (int a4 = 0; a4 < 4; ++a4)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int row = 4 * ty + a4, col = 4 * tx + b;
+                if (row < d && col < d) outp[row * d + col] = tile4_get(acc, a4, b);
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // LinearGaussian MC pass, QR-factor form, any n_vars with 5 LD^2 floats of shared memory (n_vars <= 104)
 // ------------------------------------------------------------------------------------------
 struct LinDenseShape { int ld, nt, threads, chunks, spc; size_t smem; };

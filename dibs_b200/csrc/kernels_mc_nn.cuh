@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "kernels_mc.cuh"
 #include "kernels_mc_lin_qr.cuh"   // entry_from_bits
+#include <type_traits>
 
 namespace dibs {
 
@@ -26,7 +27,8 @@ static inline int nn_threads(int d, int h) { return ((d + nn_jpw(h) - 1) / nn_jp
 // CTA size = 32 * ceil(d / (32 / H)); the bound below is what the launcher checks against
 template <int DMAX> constexpr int nn_max_threads() { return DMAX <= 32 ? 256 : (DMAX <= 64 ? 384 : 768); }
 
-template <int DMAX, int MODE>
+// HC: compile-time hidden-layer width (the node-mean shuffles unroll), 0 = runtime width
+template <int DMAX, int MODE, int HC>
 __global__ void __launch_bounds__(nn_max_threads<DMAX>()) k_mc_nn(McParams p) {
     extern __shared__ __align__(16) float smem[];
     constexpr bool HARD = (MODE == MC_THETA_HARD || MODE == MC_Z_SCORE);
@@ -88,6 +90,8 @@ __global__ void __launch_bounds__(nn_max_threads<DMAX>()) k_mc_nn(McParams p) {
     const int base_lane = jl * H;                        // first lane of this node's group
     const float inv_s2 = 1.0f / p.s2;
     const float inv_sp2 = 1.0f / p.sig2_edge;            // sig_param^2 (fill_mc maps the NN prior onto these fields)
+    const float* xcol = sX + jj;                         // x[n][j] = xcol[n * DMAX]
+    const float* keepcol = p.mask ? sKeep + jj : nullptr;
     const float w2 = on ? sTh[oW2 + jj * H + h] : 0.0f;
     const float b1 = on ? sTh[oB1 + jj * H + h] : 0.0f;
     const float b2 = on ? sTh[oB2 + jj] : 0.0f;
@@ -158,40 +162,65 @@ __global__ void __launch_bounds__(nn_max_threads<DMAX>()) k_mc_nn(McParams p) {
             }
             float gb1 = 0.0f, gw2 = 0.0f, gb2 = 0.0f, ssq = 0.0f;
             // ---- forward + backward over the observations, two per iteration (independent chains)
-            for (int n0 = 0; n0 < N; n0 += 2) {
-                const bool two = n0 + 1 < N;
+            const float onf = on ? 1.0f : 0.0f;
+            auto body = [&](int n0, auto two_c) {
+                constexpr bool TWO = decltype(two_c)::value;
                 const ulonglong2* xa = reinterpret_cast<const ulonglong2*>(sX + (size_t)n0 * DMAX);
-                const ulonglong2* xb = reinterpret_cast<const ulonglong2*>(sX + (size_t)(two ? n0 + 1 : n0) * DMAX);
+                const ulonglong2* xb = reinterpret_cast<const ulonglong2*>(sX + (size_t)(TWO ? n0 + 1 : n0) * DMAX);
                 f32x2 xva[NP], xvb[NP];
 #pragma unroll
                 for (int qd = 0; qd < DMAX / 4; ++qd) {
-                    const ulonglong2 va = xa[qd], vb = xb[qd];
+                    const ulonglong2 va = xa[qd];
                     xva[2 * qd] = va.x; xva[2 * qd + 1] = va.y;
-                    xvb[2 * qd] = vb.x; xvb[2 * qd + 1] = vb.y;
+                    if (TWO) { const ulonglong2 vb = xb[qd]; xvb[2 * qd] = vb.x; xvb[2 * qd + 1] = vb.y; }
                 }
-                f32x2 pa = pack2(b1, 0.0f), pb = pa;
+                // four independent accumulation chains (even / odd pairs of each observation)
+                f32x2 pa0 = pack2(b1, 0.0f), pa1 = 0ull, pb0 = pa0, pb1 = 0ull;
 #pragma unroll
-                for (int ip = 0; ip < NP; ++ip) { pa = fma2(xva[ip], w[ip], pa); pb = fma2(xvb[ip], w[ip], pb); }
+                for (int ip = 0; ip < NP; ip += 2) {
+                    pa0 = fma2(xva[ip], w[ip], pa0);
+                    if (ip + 1 < NP) pa1 = fma2(xva[ip + 1], w[ip + 1], pa1);
+                    if (TWO) {
+                        pb0 = fma2(xvb[ip], w[ip], pb0);
+                        if (ip + 1 < NP) pb1 = fma2(xvb[ip + 1], w[ip + 1], pb1);
+                    }
+                }
+                const f32x2 pa = add2(pa0, pa1), pb = add2(pb0, pb1);
                 const float pre_a = lo2(pa) + hi2(pa), pre_b = lo2(pb) + hi2(pb);
                 const float act_a = fmaxf(pre_a, 0.0f), act_b = fmaxf(pre_b, 0.0f);
                 const float part_a = act_a * w2, part_b = act_b * w2;
                 float mean_a = b2, mean_b = b2;
-                for (int hh = 0; hh < H; ++hh) {
-                    mean_a += __shfl_sync(0xffffffffu, part_a, base_lane + hh);
-                    mean_b += __shfl_sync(0xffffffffu, part_b, base_lane + hh);
+                if (HC > 0) {
+#pragma unroll
+                    for (int hh = 0; hh < (HC > 0 ? HC : 1); ++hh) {
+                        mean_a += __shfl_sync(0xffffffffu, part_a, base_lane + hh);
+                        if (TWO) mean_b += __shfl_sync(0xffffffffu, part_b, base_lane + hh);
+                    }
+                } else {
+                    for (int hh = 0; hh < H; ++hh) {
+                        mean_a += __shfl_sync(0xffffffffu, part_a, base_lane + hh);
+                        if (TWO) mean_b += __shfl_sync(0xffffffffu, part_b, base_lane + hh);
+                    }
                 }
-                float ra = on ? sX[(size_t)n0 * DMAX + jj] - mean_a : 0.0f;
-                float rb = (on && two) ? sX[(size_t)(n0 + 1) * DMAX + jj] - mean_b : 0.0f;
-                if (p.mask && on) { ra *= sKeep[n0 * d + jj]; if (two) rb *= sKeep[(n0 + 1) * d + jj]; }
-                ssq = fmaf(ra, ra, ssq); ssq = fmaf(rb, rb, ssq);
+                float ra = onf * (xcol[(size_t)n0 * DMAX] - mean_a);
+                float rb = TWO ? onf * (xcol[(size_t)(n0 + 1) * DMAX] - mean_b) : 0.0f;
+                if (keepcol) { ra *= keepcol[n0 * d]; if (TWO) rb *= keepcol[(n0 + 1) * d]; }
+                ssq = fmaf(ra, ra, ssq);
+                if (TWO) ssq = fmaf(rb, rb, ssq);
                 const float da = ra * inv_s2, db = rb * inv_s2;
                 const float dpa = (pre_a > 0.0f) ? da * w2 : 0.0f;
-                const float dpb = (pre_b > 0.0f) ? db * w2 : 0.0f;
+                const float dpb = (TWO && pre_b > 0.0f) ? db * w2 : 0.0f;
                 const f32x2 dpa2 = pack2(dpa, dpa), dpb2 = pack2(dpb, dpb);
 #pragma unroll
-                for (int ip = 0; ip < NP; ++ip) { gw[ip] = fma2(xva[ip], dpa2, gw[ip]); gw[ip] = fma2(xvb[ip], dpb2, gw[ip]); }
-                gb1 += dpa + dpb; gw2 = fmaf(da, act_a, gw2); gw2 = fmaf(db, act_b, gw2); gb2 += da + db;
-            }
+                for (int ip = 0; ip < NP; ++ip) {
+                    gw[ip] = fma2(xva[ip], dpa2, gw[ip]);
+                    if (TWO) gw[ip] = fma2(xvb[ip], dpb2, gw[ip]);
+                }
+                gb1 += dpa; gw2 = fmaf(da, act_a, gw2); gb2 += da;
+                if (TWO) { gb1 += dpb; gw2 = fmaf(db, act_b, gw2); gb2 += db; }
+            };
+            for (int n0 = 0; n0 + 1 < N; n0 += 2) body(n0, std::true_type{});
+            if (N & 1) body(N - 1, std::false_type{});
             // node log-prob: prior terms of the group's lanes + Gaussian likelihood
             float psum = 0.0f;
             for (int hh = 0; hh < H; ++hh) psum += __shfl_sync(0xffffffffu, prior, base_lane + hh);

@@ -16,11 +16,22 @@ static inline int nn_launch_one(K kernel, const McParams& q, dim3 grid, size_t s
     return (int)cudaGetLastError();
 }
 int DIBS_CAT(launch_mc_nn_, DIBS_DMAX)(int mode, const McParams& q, dim3 grid, size_t smem, cudaStream_t stream) {
+    // the reference's default width (hidden_layers=(5,), target.py:271) gets a specialised instance
+#if DIBS_DMAX <= 32
+    if (q.hidden == 5) {
+        switch (mode) {
+            case MC_THETA_HARD: return nn_launch_one(k_mc_nn<DIBS_DMAX, MC_THETA_HARD, 5>, q, grid, smem, stream);
+            case MC_Z_SCORE: return nn_launch_one(k_mc_nn<DIBS_DMAX, MC_Z_SCORE, 5>, q, grid, smem, stream);
+            case MC_Z_REPARAM: return nn_launch_one(k_mc_nn<DIBS_DMAX, MC_Z_REPARAM, 5>, q, grid, smem, stream);
+            default: return nn_launch_one(k_mc_nn<DIBS_DMAX, MC_LP_ONLY, 5>, q, grid, smem, stream);
+        }
+    }
+#endif
     switch (mode) {
-        case MC_THETA_HARD: return nn_launch_one(k_mc_nn<DIBS_DMAX, MC_THETA_HARD>, q, grid, smem, stream);
-        case MC_Z_SCORE: return nn_launch_one(k_mc_nn<DIBS_DMAX, MC_Z_SCORE>, q, grid, smem, stream);
-        case MC_Z_REPARAM: return nn_launch_one(k_mc_nn<DIBS_DMAX, MC_Z_REPARAM>, q, grid, smem, stream);
-        default: return nn_launch_one(k_mc_nn<DIBS_DMAX, MC_LP_ONLY>, q, grid, smem, stream);
+        case MC_THETA_HARD: return nn_launch_one(k_mc_nn<DIBS_DMAX, MC_THETA_HARD, 0>, q, grid, smem, stream);
+        case MC_Z_SCORE: return nn_launch_one(k_mc_nn<DIBS_DMAX, MC_Z_SCORE, 0>, q, grid, smem, stream);
+        case MC_Z_REPARAM: return nn_launch_one(k_mc_nn<DIBS_DMAX, MC_Z_REPARAM, 0>, q, grid, smem, stream);
+        default: return nn_launch_one(k_mc_nn<DIBS_DMAX, MC_LP_ONLY, 0>, q, grid, smem, stream);
     }
 }
 }  // namespace dibs

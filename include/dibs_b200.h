@@ -125,8 +125,9 @@ enum {
     DIBS_PHASE_ALLGATHER = 4,   /* NCCL all-gather (multi-GPU only)                          */
     DIBS_PHASE_PAIR_DIST = 5,   /* pairwise squared distances (kernel.py:30,66-71)           */
     DIBS_PHASE_PAIR_KERNEL = 6, /* exp -> K                   (kernel.py:30,66-71)           */
-    DIBS_PHASE_PHI_UPDATE = 7,  /* phi + optimizer            (svgd.py:194-224,591-670,265)  */
-    DIBS_PHASE_STEP_KEYS = 8,   /* per-particle key splits    (svgd.py:245,251,695,699,703)  */
+    DIBS_PHASE_PHI_UPDATE = 7,  /* phi partial sums per j slice (svgd.py:194-224,591-670)    */
+    DIBS_PHASE_STEP_KEYS = 8,   /* optimizer step + next step's raw scores U V^T (svgd.py:265,718-719; dibs.py:179-181);
+                                   the per-particle key splits (svgd.py:245,251,695,699,703) ride in the assemble kernel */
     DIBS_N_PHASES = 9
 };
 int dibs_svgd_steps_timed(dibs_plan* plan, int32_t t_start, int32_t n_steps, float* z, float* theta,
