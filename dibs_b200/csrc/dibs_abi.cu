@@ -117,7 +117,8 @@ struct dibs_plan {
     float* x = nullptr; int32_t* mask = nullptr;
     double* bge_r = nullptr; float* bge_table = nullptr; float* bge_coef = nullptr; int bge_r_stride = 0;
     // particle state: two packed buffers [M][ld], row = [Z | Theta | dZ | dTheta]
-    float* pk[2] = {nullptr, nullptr};
+    float* pk[2] = {nullptr, nullptr};   // particles [M][D], row = [Z | Theta], ping-pong; a rank updates its own rows
+    float* gk = nullptr;                 // log-prob gradients [M][D], row = [dZ | dTheta]
     float* v = nullptr;            // [M_loc][D]
     float* base = nullptr;         // [M_loc]
     StepState* st = nullptr;
@@ -149,7 +150,8 @@ struct dibs_plan {
     cudaEvent_t ev_join[3] = {nullptr, nullptr, nullptr};
     bool concurrent = true;
     // NCCL
-    NcclComm comm = nullptr;
+    NcclComm comm = nullptr;        // gradient rows (critical path of the step)
+    NcclComm comm_x = nullptr;      // particle rows (side branch, hidden behind the gradient phase)
     // optional per-kernel event timing (dibs_svgd_steps_timed): events recorded after each launch of an eager step
     bool timing = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -315,7 +317,7 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
     if (c.likelihood == DIBS_LIK_LINEAR_GAUSSIAN) p->Dth = p->d * p->d;
     if (c.likelihood == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN) p->Dth = p->d * (p->d * c.hidden + 2 * c.hidden + 1);
     p->D = p->Dz + p->Dth;
-    p->ld = 2 * p->D;
+    p->ld = p->D;
     p->dmax = pick_dmax(p->d);
     // fp32 constants with the reference's rounding: scale = sqrt(obs_noise); scale^2; log(2 pi scale^2)
     float scale = sqrtf(c.obs_noise);
@@ -359,6 +361,7 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
     int r = DIBS_OK;
     size_t pk_bytes = (size_t)p->M * p->ld * sizeof(float);
     if ((r = alloc((void**)&p->pk[0], pk_bytes)) || (r = alloc((void**)&p->pk[1], pk_bytes)) ||
+        (r = alloc((void**)&p->gk, pk_bytes)) ||
         (r = alloc((void**)&p->v, (size_t)p->M_loc * p->D * sizeof(float))) ||
         (r = alloc((void**)&p->base, (size_t)p->M_loc * sizeof(float))) ||
         (r = alloc((void**)&p->st, 2 * sizeof(StepState))) ||
@@ -413,6 +416,11 @@ extern "C" int dibs_plan_destroy(dibs_plan* p) {
     if (!p) return DIBS_OK;
     for (int i = 0; i < 2; ++i) if (p->gexec[i]) cudaGraphExecDestroy(p->gexec[i]);
     for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+    if (p->comm_x) {
+        cudaDeviceSynchronize();
+        if (g_nccl.CommAbort) g_nccl.CommAbort(p->comm_x);
+        else if (g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm_x);
+    }
     if (p->comm) {
         // plans are torn down whenever the host garbage-collects them, not at a point all ranks agree on: abort is
         // the non-collective teardown (ncclCommDestroy may wait for the peers); nothing is in flight after the sync
@@ -423,7 +431,7 @@ extern "C" int dibs_plan_destroy(dibs_plan* p) {
     if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
     for (int i = 0; i < 3; ++i) { if (p->aux[i]) cudaStreamDestroy(p->aux[i]); if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]); }
     for (int i = 0; i < 2; ++i) if (p->ev_fork[i]) cudaEventDestroy(p->ev_fork[i]);
-    void* ptrs[] = {p->rx_dense, p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->v, p->base, p->st, p->step_keys, p->scores,
+    void* ptrs[] = {p->rx_dense, p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->gk, p->v, p->base, p->st, p->step_keys, p->scores,
                     p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->dist_part, p->kz, p->kt, p->kfull, p->phi_part};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
@@ -826,7 +834,7 @@ static int launch_update(dibs_plan* p, const UpdateParams& u, cudaStream_t strea
     return DIBS_OK;
 }
 
-// one full _svgd_step on the packed buffers; reads pk[cur], writes the updated local rows into pk[cur^1].
+// one full _svgd_step; reads the particles pk[cur], writes the updated local rows into pk[cur^1].
 // The raw scores / sub-keys of the step were produced by the previous step's k_opt_update (or by k_prologue
 // before the first step of a call); the loop state is read from st[cur] and carried into st[cur^1].
 // `conc`: independent passes go to sibling streams (branches of the captured graph); the kernel matrix depends
@@ -835,28 +843,33 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream, bool conc) {
     float* P = p->pk[cur];
     float* Pn = p->pk[cur ^ 1];
     float* loc = P + (size_t)p->row0 * p->ld;
+    float* gloc = p->gk + (size_t)p->row0 * p->ld;
     StepState* st = p->st + cur;
+    const bool multi = p->cfg.world_size > 1;
+    if (multi && (!p->comm || !p->comm_x)) return fail(DIBS_ERR_STATE, "world_size > 1 but no NCCL communicators attached");
     if (conc) TRY(ensure_aux(p));
     PairParams q;
     fill_pair(p, q);
-    q.x_all = P; q.ld = p->ld; q.g_all = P + p->D; q.g_ld = p->ld;
-    const bool kmat_early = conc && p->cfg.world_size == 1;
-    if (kmat_early) {
-        TRY(stream_edge(stream, p->aux[2], p->ev_fork[0]));
-        TRY(launch_kmat(p, q, p->aux[2]));
+    q.x_all = P; q.ld = p->ld; q.g_all = p->gk; q.g_ld = p->ld;
+    // the kernel matrix needs the particles only: it runs on a side branch under the gradient phase; on several GPUs
+    // the branch starts with the all-gather of the particle rows every rank updated at the end of the previous step
+    cudaStream_t s_k = conc ? p->aux[2] : stream;
+    if (conc) TRY(stream_edge(stream, s_k, p->ev_fork[0]));
+    if (multi) {
+        NC(g_nccl.AllGather(loc, P, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm_x, s_k));
+        mark(p, s_k, DIBS_PHASE_ALLGATHER);
     }
+    TRY(launch_kmat(p, q, s_k));
     Src s{loc, p->ld, p->Dth ? loc + p->Dz : nullptr, p->ld, p->M_loc, p->row0, st, nullptr, 0, p->step_keys, p->scores};
     TRY(enqueue_grads(p, s, p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->base, p->base,
-                      loc + p->D, p->ld, p->Dth ? loc + p->D + p->Dz : nullptr, p->ld, stream, conc, p->step_keys,
+                      gloc, p->ld, p->Dth ? gloc + p->Dz : nullptr, p->ld, stream, conc, p->step_keys,
                       p->st + (cur ^ 1)));
-    if (p->cfg.world_size > 1) {
-        if (!p->comm) return fail(DIBS_ERR_STATE, "world_size > 1 but no NCCL communicator attached");
-        // the one exchange of the step: every rank contributes its rows [Z | Theta | dZ | dTheta] (in place)
-        NC(g_nccl.AllGather(loc, P, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm, stream));
+    if (multi) {
+        // the one exchange on the critical path: every rank contributes its gradient rows [dZ | dTheta] (in place)
+        NC(g_nccl.AllGather(gloc, p->gk, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm, stream));
         mark(p, stream, DIBS_PHASE_ALLGATHER);
     }
-    if (kmat_early) TRY(stream_edge(p->aux[2], stream, p->ev_join[2]));
-    else TRY(launch_kmat(p, q, stream));
+    if (conc) TRY(stream_edge(s_k, stream, p->ev_join[2]));
     TRY(launch_phi(p, q, stream));
     UpdateParams u;
     fill_update(p, q, u);
@@ -905,8 +918,9 @@ static int svgd_steps_impl(dibs_plan* p, int32_t t_start, int32_t n_steps, float
         if (p->cfg.world_size > 1) {
             // warm NCCL up outside the capture (first-use allocations and connection set-up are not capturable);
             // pk[1] holds nothing yet, so an in-place all-gather on it is harmless
-            if (!p->comm) return fail(DIBS_ERR_STATE, "world_size > 1 but no NCCL communicator attached");
-            NC(g_nccl.AllGather(p->pk[1] + (size_t)p->row0 * p->ld, p->pk[1], (size_t)p->M_loc * p->ld, 7, p->comm, stream));
+            if (!p->comm || !p->comm_x) return fail(DIBS_ERR_STATE, "world_size > 1 but no NCCL communicators attached");
+            NC(g_nccl.AllGather(p->pk[1] + (size_t)p->row0 * p->ld, p->pk[1], (size_t)p->M_loc * p->ld, 7, p->comm_x, stream));
+            NC(g_nccl.AllGather(p->gk + (size_t)p->row0 * p->ld, p->gk, (size_t)p->M_loc * p->ld, 7, p->comm, stream));
             CU(cudaStreamSynchronize(stream));
         }
         for (int par = 0; par < 2; ++par) {
@@ -1003,7 +1017,8 @@ extern "C" int dibs_plan_attach_nccl(dibs_plan* p, const uint8_t* id128) {
     TRY(nccl_load());
     NcclId id;
     memcpy(id.internal, id128, 128);
-    NC(g_nccl.CommInitRank(&p->comm, p->cfg.world_size, id, p->cfg.rank));
+    // first call: communicator of the gradient exchange; second call (another unique id): the particle exchange
+    NC(g_nccl.CommInitRank(p->comm ? &p->comm_x : &p->comm, p->cfg.world_size, id, p->cfg.rank));
     return DIBS_OK;
 }
 

@@ -323,6 +323,12 @@ class _Plan:
         self.theta_dim = nat.lib().dibs_theta_dim(handle)
 
     def attach_nccl(self):
+        """Two communicators: the gradient exchange (critical path) and the particle exchange (side branch of the
+        step graph) -- independent communicators, so the two may run in either order on different ranks."""
+        self._attach_one()
+        self._attach_one()
+
+    def _attach_one(self):
         import torch.distributed as dist
         dev = self.owner.device
         ident = torch.zeros(128, dtype=torch.uint8)
