@@ -39,6 +39,8 @@ PROTOTYPES = {
     "dibs_set_data": (ctypes.c_int, [_P, _P, _P, _I, _P, _P]),
     "dibs_nccl_unique_id": (ctypes.c_int, [_P]),
     "dibs_plan_attach_nccl": (ctypes.c_int, [_P, _P]),
+    "dibs_plan_ipc_export": (ctypes.c_int, [_P, _P]),
+    "dibs_plan_ipc_attach": (ctypes.c_int, [_P, _P]),
     "dibs_svgd_steps": (ctypes.c_int, [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "dibs_svgd_steps_timed": (ctypes.c_int, [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, ctypes.c_int64, _P, _P]),
     "dibs_init_particles": (ctypes.c_int, [_P, _P, _P, _P, _P]),

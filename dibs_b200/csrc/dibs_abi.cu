@@ -118,7 +118,16 @@ struct dibs_plan {
     double* bge_r = nullptr; float* bge_table = nullptr; float* bge_coef = nullptr; int bge_r_stride = 0;
     // particle state: two packed buffers [M][ld], row = [Z | Theta | dZ | dTheta]
     float* pk[2] = {nullptr, nullptr};   // particles [M][D], row = [Z | Theta], ping-pong; a rank updates its own rows
-    float* gk = nullptr;                 // log-prob gradients [M][D], row = [dZ | dTheta]
+    float* gk[2] = {nullptr, nullptr};   // log-prob gradients [M][D], row = [dZ | dTheta], by step parity
+    // peer-memory exchange (kernels_peer.cuh): flags / epochs / counters, and the peers' buffers opened through CUDA IPC
+    uint32_t* peer_flags_local = nullptr;   // [PEER_KINDS][PEER_MAX]
+    uint32_t* peer_epoch = nullptr;         // [PEER_KINDS]
+    uint32_t* peer_counter = nullptr;       // [PEER_KINDS]
+    bool p2p = false;
+    float* peer_pk[2][PEER_MAX] = {};
+    float* peer_gk[2][PEER_MAX] = {};
+    uint32_t* peer_flags[PEER_MAX] = {};
+    std::vector<void*> ipc_opened;
     float* v = nullptr;            // [M_loc][D]
     float* base = nullptr;         // [M_loc]
     StepState* st = nullptr;
@@ -317,7 +326,7 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
     if (c.likelihood == DIBS_LIK_LINEAR_GAUSSIAN) p->Dth = p->d * p->d;
     if (c.likelihood == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN) p->Dth = p->d * (p->d * c.hidden + 2 * c.hidden + 1);
     p->D = p->Dz + p->Dth;
-    p->ld = p->D;
+    p->ld = (p->D + 3) & ~3;                 // row stride: a multiple of 4 floats (128-bit pushes / loads)
     p->dmax = pick_dmax(p->d);
     // fp32 constants with the reference's rounding: scale = sqrt(obs_noise); scale^2; log(2 pi scale^2)
     float scale = sqrtf(c.obs_noise);
@@ -359,9 +368,13 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
         return DIBS_OK;
     };
     int r = DIBS_OK;
-    size_t pk_bytes = (size_t)p->M * p->ld * sizeof(float);
+    // buffers that may be shared through CUDA IPC get whole 2 MiB blocks of their own
+    size_t pk_bytes = (((size_t)p->M * p->ld * sizeof(float)) + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
     if ((r = alloc((void**)&p->pk[0], pk_bytes)) || (r = alloc((void**)&p->pk[1], pk_bytes)) ||
-        (r = alloc((void**)&p->gk, pk_bytes)) ||
+        (r = alloc((void**)&p->gk[0], pk_bytes)) || (r = alloc((void**)&p->gk[1], pk_bytes)) ||
+        (r = alloc((void**)&p->peer_flags_local, 2u << 20)) ||
+        (r = alloc((void**)&p->peer_epoch, PEER_KINDS * sizeof(uint32_t))) ||
+        (r = alloc((void**)&p->peer_counter, PEER_KINDS * sizeof(uint32_t))) ||
         (r = alloc((void**)&p->v, (size_t)p->M_loc * p->D * sizeof(float))) ||
         (r = alloc((void**)&p->base, (size_t)p->M_loc * sizeof(float))) ||
         (r = alloc((void**)&p->st, 2 * sizeof(StepState))) ||
@@ -416,6 +429,10 @@ extern "C" int dibs_plan_destroy(dibs_plan* p) {
     if (!p) return DIBS_OK;
     for (int i = 0; i < 2; ++i) if (p->gexec[i]) cudaGraphExecDestroy(p->gexec[i]);
     for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+    if (!p->ipc_opened.empty()) {
+        cudaDeviceSynchronize();
+        for (void* q : p->ipc_opened) cudaIpcCloseMemHandle(q);
+    }
     if (p->comm_x) {
         cudaDeviceSynchronize();
         if (g_nccl.CommAbort) g_nccl.CommAbort(p->comm_x);
@@ -431,7 +448,7 @@ extern "C" int dibs_plan_destroy(dibs_plan* p) {
     if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
     for (int i = 0; i < 3; ++i) { if (p->aux[i]) cudaStreamDestroy(p->aux[i]); if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]); }
     for (int i = 0; i < 2; ++i) if (p->ev_fork[i]) cudaEventDestroy(p->ev_fork[i]);
-    void* ptrs[] = {p->rx_dense, p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->gk, p->v, p->base, p->st, p->step_keys, p->scores,
+    void* ptrs[] = {p->rx_dense, p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->gk[0], p->gk[1], p->peer_flags_local, p->peer_epoch, p->peer_counter, p->v, p->base, p->st, p->step_keys, p->scores,
                     p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->dist_part, p->kz, p->kt, p->kfull, p->phi_part};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
@@ -742,7 +759,8 @@ static int ensure_aux(dibs_plan* p) {
 // gradient phase for `s.n` particles: MC passes | acyclicity (independent: sibling streams when `conc`) -> assemble
 static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_stats, float* z_acc, float* z_stats,
                          float* acyc, const float* base_in, float* base_out, float* grad_z, int gz_ld, float* grad_th,
-                         int gth_ld, cudaStream_t stream, bool conc, uint32_t* next_keys, StepState* st_next) {
+                         int gth_ld, cudaStream_t stream, bool conc, uint32_t* next_keys, StepState* st_next,
+                         const PeerPush* push = nullptr) {
     const bool joint = p->cfg.joint;
     const McShape sh = mc_shape(p, s.n, p->cfg.n_grad_mc_samples, false);
     McParams q;
@@ -781,6 +799,7 @@ static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_st
     a.next_keys = next_keys; a.st_next = st_next;
     a.n_step_splits = joint ? 3 : 2; a.n_particles = p->M; a.partitionable = p->cfg.prng_partitionable;
     a.m_offset = s.m_offset; a.pre_split_mask = joint ? 2u : 1u;
+    if (push) a.push = *push;
     TRY(launch_asm(p, a, stream));
     mark(p, stream, DIBS_PHASE_ASSEMBLE);
     return DIBS_OK;
@@ -839,34 +858,71 @@ static int launch_update(dibs_plan* p, const UpdateParams& u, cudaStream_t strea
 // before the first step of a call); the loop state is read from st[cur] and carried into st[cur^1].
 // `conc`: independent passes go to sibling streams (branches of the captured graph); the kernel matrix depends
 // on the particles only, so on a single GPU it overlaps the whole gradient phase.
+static void fill_push(const dibs_plan* p, PeerPush& pp, int kind, float* const* dst) {
+    memset(&pp, 0, sizeof(pp));
+    pp.world = p->cfg.world_size; pp.rank = p->cfg.rank; pp.kind = kind;
+    for (int q = 0; q < pp.world; ++q) { pp.dst[q] = dst ? dst[q] : nullptr; pp.flags[q] = p->peer_flags[q]; }
+    pp.epoch = p->peer_epoch; pp.counter = p->peer_counter;
+}
+
+// push this rank's rows of `local` (and/or just raise the flag of `kind`) to every peer
+static int launch_push(dibs_plan* p, int kind, const float* local, float* const* peer_bufs, cudaStream_t stream) {
+    PeerPush pp;
+    fill_push(p, pp, kind, peer_bufs);
+    const size_t off4 = local ? (size_t)p->row0 * p->ld / 4 : 0, n4 = local ? (size_t)p->M_loc * p->ld / 4 : 0;
+    int blocks = (int)((n4 + 1023) / 1024);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 2 * 148) blocks = 2 * 148;
+    k_peer_push<<<blocks, 256, 0, stream>>>(pp, reinterpret_cast<const float4*>(local), off4, n4);
+    LAUNCHED();
+    return DIBS_OK;
+}
+
+static PeerWait make_wait(const dibs_plan* p, int kind) {
+    PeerWait w;
+    w.flags = p->p2p ? p->peer_flags_local : nullptr; w.epoch = p->peer_epoch; w.world = p->cfg.world_size; w.kind = kind;
+    return w;
+}
+
 static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream, bool conc) {
     float* P = p->pk[cur];
     float* Pn = p->pk[cur ^ 1];
+    float* G = p->gk[cur];
     float* loc = P + (size_t)p->row0 * p->ld;
-    float* gloc = p->gk + (size_t)p->row0 * p->ld;
+    float* gloc = G + (size_t)p->row0 * p->ld;
     StepState* st = p->st + cur;
     const bool multi = p->cfg.world_size > 1;
-    if (multi && (!p->comm || !p->comm_x)) return fail(DIBS_ERR_STATE, "world_size > 1 but no NCCL communicators attached");
+    if (multi && !p->p2p && (!p->comm || !p->comm_x))
+        return fail(DIBS_ERR_STATE, "world_size > 1 but neither peer memory nor NCCL communicators are attached");
     if (conc) TRY(ensure_aux(p));
     PairParams q;
     fill_pair(p, q);
-    q.x_all = P; q.ld = p->ld; q.g_all = p->gk; q.g_ld = p->ld;
+    q.x_all = P; q.ld = p->ld; q.g_all = G; q.g_ld = p->ld;
+    q.wait_x = make_wait(p, PEER_KIND_X); q.wait_g = make_wait(p, PEER_KIND_GRAD);
     // the kernel matrix needs the particles only: it runs on a side branch under the gradient phase; on several GPUs
-    // the branch starts with the all-gather of the particle rows every rank updated at the end of the previous step
+    // the particle rows every rank updated at the end of the previous step arrive by peer pushes (the kernel waits
+    // on their flags) or, on the NCCL path, by an all-gather at the head of the branch
     cudaStream_t s_k = conc ? p->aux[2] : stream;
     if (conc) TRY(stream_edge(stream, s_k, p->ev_fork[0]));
-    if (multi) {
+    if (multi && !p->p2p) {
         NC(g_nccl.AllGather(loc, P, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm_x, s_k));
         mark(p, s_k, DIBS_PHASE_ALLGATHER);
     }
     TRY(launch_kmat(p, q, s_k));
     Src s{loc, p->ld, p->Dth ? loc + p->Dz : nullptr, p->ld, p->M_loc, p->row0, st, nullptr, 0, p->step_keys, p->scores};
+    // peer-memory path: the producing kernels store their rows into every peer themselves (fused exchange) unless
+    // DIBS_B200_PUSH_KERNEL=1 asks for the separate copy kernel
+    static const bool fused_push = !(getenv("DIBS_B200_PUSH_KERNEL") && getenv("DIBS_B200_PUSH_KERNEL")[0] == '1');
+    const bool fuse = multi && p->p2p && fused_push;
+    PeerPush push_g, push_x;
+    if (fuse) { fill_push(p, push_g, PEER_KIND_GRAD, p->peer_gk[cur]); fill_push(p, push_x, PEER_KIND_X, p->peer_pk[cur ^ 1]); }
     TRY(enqueue_grads(p, s, p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->base, p->base,
                       gloc, p->ld, p->Dth ? gloc + p->Dz : nullptr, p->ld, stream, conc, p->step_keys,
-                      p->st + (cur ^ 1)));
-    if (multi) {
-        // the one exchange on the critical path: every rank contributes its gradient rows [dZ | dTheta] (in place)
-        NC(g_nccl.AllGather(gloc, p->gk, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm, stream));
+                      p->st + (cur ^ 1), fuse ? &push_g : nullptr));
+    if (multi && !fuse) {
+        // the one exchange on the critical path: every rank contributes its gradient rows [dZ | dTheta]
+        if (p->p2p) TRY(launch_push(p, PEER_KIND_GRAD, G, p->peer_gk[cur], stream));
+        else NC(g_nccl.AllGather(gloc, G, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm, stream));
         mark(p, stream, DIBS_PHASE_ALLGATHER);
     }
     if (conc) TRY(stream_edge(s_k, stream, p->ev_join[2]));
@@ -876,7 +932,13 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream, bool conc) {
     u.x_next = Pn + (size_t)p->row0 * p->ld; u.next_ld = p->ld;
     u.v = p->v; u.v_ld = p->D;
     u.scores = p->scores;
+    u.row0 = p->row0;
+    if (fuse) u.push = push_x;
     TRY(launch_update(p, u, stream));
+    if (multi && p->p2p && !fuse) {
+        TRY(launch_push(p, PEER_KIND_X, Pn, p->peer_pk[cur ^ 1], stream));
+        mark(p, stream, DIBS_PHASE_ALLGATHER);
+    }
     return DIBS_OK;
 }
 
@@ -905,8 +967,14 @@ static int svgd_steps_impl(dibs_plan* p, int32_t t_start, int32_t n_steps, float
         if (p->Dth) CU(cudaMemcpy2DAsync(p->v + p->Dz, fd, v_theta, ft, ft, p->M_loc, cudaMemcpyDeviceToDevice, stream));
     }
     CU(cudaMemcpyAsync(p->base, sf_baseline, sizeof(float) * p->M_loc, cudaMemcpyDeviceToDevice, stream));
+    if (p->p2p) {
+        // call-level barrier: no peer may still be reading the rows this call is about to overwrite
+        k_peer_wait<<<1, 32, 0, stream>>>(make_wait(p, PEER_KIND_DONE));
+        LAUNCHED();
+    }
     k_set_state<<<1, 1, 0, stream>>>(p->st, key, t_start);
     LAUNCHED();
+    if (p->p2p) TRY(launch_push(p, PEER_KIND_X, p->pk[0], p->peer_pk[0], stream));   // first step's particle rows
     // scores and sub-keys of the first step; later steps get theirs from the previous step's k_opt_update
     TRY(launch_prologue(p, loc0, p->ld, p->M_loc, p->row0, p->st, nullptr, p->cfg.joint ? 3 : 2, p->cfg.joint ? 2u : 1u,
                         p->scores, p->step_keys, stream));
@@ -915,12 +983,12 @@ static int svgd_steps_impl(dibs_plan* p, int32_t t_start, int32_t n_steps, float
     const bool graph = p->use_graph && (p->cfg.world_size == 1 || nccl_graph) && !(timed && per_kernel);
     p->ev_used = 0;
     if (graph && !p->gexec[0]) {
-        if (p->cfg.world_size > 1) {
+        if (p->cfg.world_size > 1 && !p->p2p) {
             // warm NCCL up outside the capture (first-use allocations and connection set-up are not capturable);
             // pk[1] holds nothing yet, so an in-place all-gather on it is harmless
             if (!p->comm || !p->comm_x) return fail(DIBS_ERR_STATE, "world_size > 1 but no NCCL communicators attached");
             NC(g_nccl.AllGather(p->pk[1] + (size_t)p->row0 * p->ld, p->pk[1], (size_t)p->M_loc * p->ld, 7, p->comm_x, stream));
-            NC(g_nccl.AllGather(p->gk + (size_t)p->row0 * p->ld, p->gk, (size_t)p->M_loc * p->ld, 7, p->comm, stream));
+            NC(g_nccl.AllGather(p->gk[1] + (size_t)p->row0 * p->ld, p->gk[1], (size_t)p->M_loc * p->ld, 7, p->comm, stream));
             CU(cudaStreamSynchronize(stream));
         }
         for (int par = 0; par < 2; ++par) {
@@ -944,6 +1012,17 @@ static int svgd_steps_impl(dibs_plan* p, int32_t t_start, int32_t n_steps, float
         if (timed) {
             // cold-L2 protocol: overwrite a buffer larger than L2 (untimed), then bracket the step with events
             if (flush_buf) CU(cudaMemsetAsync(flush_buf, i & 0xff, flush_bytes, stream));
+            if (flush_buf && p->cfg.world_size > 1) {
+                // the flush takes a different time on every rank: line the ranks up again before the bracket opens,
+                // otherwise a step is charged the peers' flush while it waits for their rows
+                if (p->p2p) {
+                    TRY(launch_push(p, PEER_KIND_SYNC, nullptr, nullptr, stream));
+                    k_peer_wait<<<1, 32, 0, stream>>>(make_wait(p, PEER_KIND_SYNC));
+                    LAUNCHED();
+                } else {
+                    NC(g_nccl.AllGather(p->peer_epoch, p->peer_flags_local, 1, 7, p->comm, stream));
+                }
+            }
             p->timing = true;
             mark(p, stream, -1);
             p->timing = per_kernel != 0;
@@ -978,6 +1057,7 @@ static int svgd_steps_impl(dibs_plan* p, int32_t t_start, int32_t n_steps, float
         if (p->Dth) CU(cudaMemcpy2DAsync(v_theta, ft, p->v + p->Dz, fd, ft, p->M_loc, cudaMemcpyDeviceToDevice, stream));
     }
     CU(cudaMemcpyAsync(sf_baseline, p->base, sizeof(float) * p->M_loc, cudaMemcpyDeviceToDevice, stream));
+    if (p->p2p) TRY(launch_push(p, PEER_KIND_DONE, nullptr, nullptr, stream));
     k_get_key<<<1, 1, 0, stream>>>(p->st + (n_steps & 1), key);
     LAUNCHED();
     return DIBS_OK;
@@ -1019,6 +1099,49 @@ extern "C" int dibs_plan_attach_nccl(dibs_plan* p, const uint8_t* id128) {
     memcpy(id.internal, id128, 128);
     // first call: communicator of the gradient exchange; second call (another unique id): the particle exchange
     NC(g_nccl.CommInitRank(p->comm ? &p->comm_x : &p->comm, p->cfg.world_size, id, p->cfg.rank));
+    return DIBS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// peer-memory exchange set-up (CUDA IPC between the ranks of one node)
+// ------------------------------------------------------------------------------------------
+static const int IPC_BUFS = 5;   // pk[0], pk[1], gk[0], gk[1], flags
+
+extern "C" int dibs_plan_ipc_export(dibs_plan* p, uint8_t* handles_out) {
+    if (!p || !handles_out) return fail(DIBS_ERR_INVALID_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* bufs[IPC_BUFS] = {p->pk[0], p->pk[1], p->gk[0], p->gk[1], p->peer_flags_local};
+    for (int i = 0; i < IPC_BUFS; ++i) {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, bufs[i]));
+        memcpy(handles_out + 64 * i, &h, 64);
+    }
+    return DIBS_OK;
+}
+
+extern "C" int dibs_plan_ipc_attach(dibs_plan* p, const uint8_t* all_handles) {
+    if (!p || !all_handles) return fail(DIBS_ERR_INVALID_ARG, "null argument");
+    const int W = p->cfg.world_size;
+    if (W < 2 || W > PEER_MAX) return fail(DIBS_ERR_UNSUPPORTED, "peer-memory exchange needs 2..16 ranks");
+    for (int q = 0; q < W; ++q) {
+        void* opened[IPC_BUFS];
+        if (q == p->cfg.rank) {
+            void* mine[IPC_BUFS] = {p->pk[0], p->pk[1], p->gk[0], p->gk[1], p->peer_flags_local};
+            memcpy(opened, mine, sizeof(mine));
+        } else {
+            for (int i = 0; i < IPC_BUFS; ++i) {
+                cudaIpcMemHandle_t h;
+                memcpy(&h, all_handles + ((size_t)q * IPC_BUFS + i) * 64, 64);
+                CU(cudaIpcOpenMemHandle(&opened[i], h, cudaIpcMemLazyEnablePeerAccess));
+                p->ipc_opened.push_back(opened[i]);
+            }
+        }
+        p->peer_pk[0][q] = (float*)opened[0]; p->peer_pk[1][q] = (float*)opened[1];
+        p->peer_gk[0][q] = (float*)opened[2]; p->peer_gk[1][q] = (float*)opened[3];
+        p->peer_flags[q] = (uint32_t*)opened[4];
+    }
+    for (int i = 0; i < 2; ++i) if (p->gexec[i]) { cudaGraphExecDestroy(p->gexec[i]); p->gexec[i] = nullptr; }
+    p->p2p = true;
     return DIBS_OK;
 }
 

@@ -7,6 +7,7 @@
 // like the reference's autodiff so that near-neighbours do not cancel.
 #pragma once
 #include "common.cuh"
+#include "kernels_peer.cuh"
 
 namespace dibs {
 
@@ -21,6 +22,7 @@ struct PairParams {
     float* dist_part;                    // [n_split][n_rows][n_all] partial squared distances
     int n_jsplit, j_len;                 // phi: slices of the j axis (j_len on the global index, multiple of 32)
     float* phi_part;                     // [n_jsplit][n_rows][dz+dth] per-slice sums of drive - (2/h) repulsion
+    PeerWait wait_x, wait_g;             // peer-memory exchange: flags to wait on before reading x_all / g_all
     float* kz; float* kt; float* kfull;  // [n_rows][n_all]
     float h_z, h_t, scale_z, scale_t;
 };
@@ -36,6 +38,7 @@ constexpr int KFP = 36;   // padded row stride (floats): 16-byte aligned, quarte
 __global__ void __launch_bounds__(256) k_pair_dist(PairParams p) {
     __shared__ __align__(16) float sI[KT * KFP];
     __shared__ __align__(16) float sJ[KT * KFP];
+    peer_wait(p.wait_x);
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int j0 = blockIdx.x * KT, i0 = blockIdx.y * KT, sp = blockIdx.z;
     const bool z_part = sp < p.n_split_z;
@@ -143,6 +146,7 @@ __global__ void __launch_bounds__(128) k_phi_partial(PairParams p) {
     __shared__ __align__(16) float sKt[PT_J * PT_KP * 2];    // K term (z or theta block)
     __shared__ __align__(16) float sXj[PT_J * PT_C];
     __shared__ __align__(16) float sGj[PT_J * PT_C];
+    peer_wait(p.wait_g);
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int i0 = blockIdx.y * PT_I;
     const int D = p.dz + p.dth;
@@ -257,6 +261,8 @@ struct UpdateParams {
     // next step's raw scores U V^T (null: skip)
     int d, k;
     float* scores;
+    // peer-memory exchange fused into the kernel: the updated row also goes into every peer's particle buffer
+    int row0; PeerPush push;
 };
 
 __global__ void __launch_bounds__(256) k_opt_update(UpdateParams p) {
@@ -285,12 +291,14 @@ __global__ void __launch_bounds__(256) k_opt_update(UpdateParams p) {
                 x = __fsub_rn(x, __fmul_rn(p.stepsize, phi));   // sgd: x - step * g
             }
             p.x_next[(size_t)m * p.next_ld + e] = x;
+            if (p.push.world) peer_store(p.push, (size_t)(p.row0 + m) * p.next_ld + e, x);
         }
         if (p.scores && e < p.dz) {
             const int i = e / (2 * k), r = e - i * 2 * k, kk = r >> 1;
             ((r & 1) ? sV : sU)[kk * d + i] = x;
         }
     }
+    if (p.push.world) peer_signal(p.push, gridDim.x);
     if (!p.scores) return;
     __syncthreads();
     float* out = p.scores + (size_t)m * d * d;

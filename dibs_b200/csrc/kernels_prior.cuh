@@ -8,6 +8,7 @@
 // dibs.py:376-385,451-457,531-549.
 #pragma once
 #include "common.cuh"
+#include "kernels_peer.cuh"
 
 namespace dibs {
 
@@ -228,6 +229,9 @@ struct AsmParams {
     // next step's loop state and per-pass sub-keys (step loop only; null: skip)
     uint32_t* next_keys; StepState* st_next;
     int n_step_splits, n_particles, partitionable, m_offset; uint32_t pre_split_mask;
+    // peer-memory exchange fused into the kernel: every gradient value is also stored into the same row of each
+    // peer's gradient buffer, the last CTA raises the flags (push.world == 0: off)
+    PeerPush push;
 };
 
 // merged softmax normaliser of the chunk partials: weights w_c = exp(m_c - max) / sum_c l_c exp(m_c - max) into sW[c]
@@ -344,6 +348,7 @@ __global__ void __launch_bounds__(256) k_assemble_grad(AsmParams p) {
             float num = 0.0f;
             for (int c = 0; c < p.th_chunks; ++c) num = fmaf(ta[(size_t)c * p.th_dim + e], sWt[c], num);
             gth[e] = num;
+            if (p.push.world) peer_store(p.push, (size_t)(p.m_offset + m) * p.gth_ld + 2 * d * k + e, num);
         }
     }
     __syncthreads();
@@ -363,6 +368,10 @@ __global__ void __launch_bounds__(256) k_assemble_grad(AsmParams p) {
             dv -= sZ[2 * e + 1] / p.sigma_z2;
         }
         gz[2 * e] = du; gz[2 * e + 1] = dv;
+        if (p.push.world) {
+            const size_t off = (size_t)(p.m_offset + m) * p.gz_ld + 2 * e;
+            peer_store(p.push, off, du); peer_store(p.push, off + 1, dv);
+        }
     }
     if (p.zacc && p.baselines_out && tid == 0) {
         const float b_in = p.baselines_in ? p.baselines_in[m] : 0.0f;
@@ -370,6 +379,7 @@ __global__ void __launch_bounds__(256) k_assemble_grad(AsmParams p) {
         p.baselines_out[m] = (p.z_mode == MC_Z_SCORE)
             ? p.sf_coef * (sMisc[0] / (float)p.n_samples) + (1.0f - p.sf_coef) * b_in : b_in;
     }
+    if (p.push.world) peer_signal(p.push, gridDim.x);
 }
 
 inline size_t assemble_smem(int d, int k, int z_chunks, int th_chunks) {

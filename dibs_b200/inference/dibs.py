@@ -9,6 +9,8 @@ Python/PyTorch implementation of the math and no fallback.  Arrays are torch CUD
 """
 import ctypes
 
+import os
+
 import numpy as np
 import torch
 
@@ -325,8 +327,40 @@ class _Plan:
     def attach_nccl(self):
         """Two communicators: the gradient exchange (critical path) and the particle exchange (side branch of the
         step graph) -- independent communicators, so the two may run in either order on different ranks."""
+        if os.environ.get("DIBS_B200_NO_P2P") != "1" and self._attach_peer_memory():
+            return                      # rows travel by peer-memory pushes: no communicator needed
         self._attach_one()
         self._attach_one()
+
+    def _attach_peer_memory(self):
+        """Exchange CUDA-IPC handles of the plan's particle / gradient / flag buffers and open the peers' copies: the
+        step then pushes rows over NVLink peer memory instead of calling NCCL (kernels_peer.cuh).  All ranks take
+        the same branch: the outcome of the local attach is agreed on with an all-reduce."""
+        import torch.distributed as dist
+        dev = self.owner.device
+        world = self.cfg.world_size
+        mine = np.zeros(320, np.uint8)
+        ok = 1
+        with torch.cuda.device(dev):
+            if nat.lib().dibs_plan_ipc_export(self.handle, nat.ptr(mine)) != 0:
+                ok = 0
+        on_gpu = dist.get_backend() == "nccl"
+        blob = torch.from_numpy(mine).to(dev) if on_gpu else torch.from_numpy(mine)
+        allb = torch.empty(world * 320, dtype=torch.uint8, device=blob.device)
+        dist.all_gather_into_tensor(allb, blob)
+        flag = torch.tensor([ok], dtype=torch.int32, device=blob.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) != 1:
+            return False
+        buf = np.ascontiguousarray(allb.cpu().numpy())
+        with torch.cuda.device(dev):
+            ok = 1 if nat.lib().dibs_plan_ipc_attach(self.handle, nat.ptr(buf)) == 0 else 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=blob.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)       # also the barrier: every rank has opened its peers
+        if int(flag.item()) != 1:
+            raise RuntimeError("dibs_b200: CUDA IPC attach succeeded on some ranks only: " +
+                               nat.lib().dibs_last_error().decode())
+        return True
 
     def _attach_one(self):
         import torch.distributed as dist

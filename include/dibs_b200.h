@@ -98,6 +98,12 @@ int dibs_set_data(dibs_plan* plan, const float* x, const int32_t* interv_mask, i
  * at run time with dlopen("libnccl.so.2") (the copy torch already loaded). */
 int dibs_nccl_unique_id(uint8_t* id128_host);
 int dibs_plan_attach_nccl(dibs_plan* plan, const uint8_t* id128_host);
+/* Peer-memory exchange (preferred on one NVSwitch node): each rank exports CUDA-IPC handles of its particle /
+ * gradient / flag buffers (5 x 64 bytes), the host all-gathers them, every rank opens its peers' buffers; the
+ * step then pushes rows straight into peer memory instead of calling NCCL.  handles_out: 320 bytes;
+ * all_handles: world_size x 320 bytes in rank order. */
+int dibs_plan_ipc_export(dibs_plan* plan, uint8_t* handles_out_host);
+int dibs_plan_ipc_attach(dibs_plan* plan, const uint8_t* all_handles_host);
 
 /* ---- the hot loop ---------------------------------------------------------------------------
  * replaces: _svgd_loop -> lax.fori_loop over _svgd_step (svgd.py:226-272, 673-727).
