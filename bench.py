@@ -271,7 +271,8 @@ def config_dict(name, n_gpus):
     return {"workload": f"{name}: {desc}", "n_vars": d, "n_particles": m, "n_grad_mc_samples": s,
             "n_acyclicity_mc_samples": a, "n_observations": N_OBS, "graph_prior": f"er(n_edges_per_node={er_edges(d)})",
             "optimizer": "rmsprop(0.005)", "t_start": T_MID, "particles_per_gpu": m // n_gpus,
-            "parallelism": f"particle-sharded x{n_gpus}, one all-gather per step" if n_gpus > 1 else "single GPU",
+            "parallelism": (f"particle-sharded x{n_gpus}; rows exchanged by peer-memory pushes over NVLink (particles under the "
+                            "gradient phase, gradients on the critical path), NCCL all-gathers as fallback") if n_gpus > 1 else "single GPU",
             "l2": f"flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB memset outside the event bracket)"}
 
 

@@ -407,7 +407,7 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
     {
         const int col_tiles = ceil_div(p->Dz, PT_C) + ceil_div(p->Dth, PT_C);
         const int row_scale = p->M / 256 > 1 ? p->M / 256 : 1;
-        int ns = ceil_div(296, col_tiles * row_scale);
+        int ns = ceil_div(592, col_tiles * row_scale);
         const int max_ns = p->M / 64 > 1 ? p->M / 64 : 1;
         if (ns > max_ns) ns = max_ns;
         if (ns < 1) ns = 1;
@@ -904,8 +904,11 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream, bool conc) {
     // on their flags) or, on the NCCL path, by an all-gather at the head of the branch
     cudaStream_t s_k = conc ? p->aux[2] : stream;
     if (conc) TRY(stream_edge(stream, s_k, p->ev_fork[0]));
-    if (multi && !p->p2p) {
-        NC(g_nccl.AllGather(loc, P, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm_x, s_k));
+    if (multi) {
+        // the branch starts by publishing the rows this rank updated at the end of the previous step (or packed at
+        // the start of the call): off the critical path, under the gradient phase
+        if (p->p2p) TRY(launch_push(p, PEER_KIND_X, P, p->peer_pk[cur], s_k));
+        else NC(g_nccl.AllGather(loc, P, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm_x, s_k));
         mark(p, s_k, DIBS_PHASE_ALLGATHER);
     }
     TRY(launch_kmat(p, q, s_k));
@@ -914,8 +917,8 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream, bool conc) {
     // DIBS_B200_PUSH_KERNEL=1 asks for the separate copy kernel
     static const bool fused_push = !(getenv("DIBS_B200_PUSH_KERNEL") && getenv("DIBS_B200_PUSH_KERNEL")[0] == '1');
     const bool fuse = multi && p->p2p && fused_push;
-    PeerPush push_g, push_x;
-    if (fuse) { fill_push(p, push_g, PEER_KIND_GRAD, p->peer_gk[cur]); fill_push(p, push_x, PEER_KIND_X, p->peer_pk[cur ^ 1]); }
+    PeerPush push_g;
+    if (fuse) fill_push(p, push_g, PEER_KIND_GRAD, p->peer_gk[cur]);
     TRY(enqueue_grads(p, s, p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->base, p->base,
                       gloc, p->ld, p->Dth ? gloc + p->Dz : nullptr, p->ld, stream, conc, p->step_keys,
                       p->st + (cur ^ 1), fuse ? &push_g : nullptr));
@@ -933,12 +936,7 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream, bool conc) {
     u.v = p->v; u.v_ld = p->D;
     u.scores = p->scores;
     u.row0 = p->row0;
-    if (fuse) u.push = push_x;
     TRY(launch_update(p, u, stream));
-    if (multi && p->p2p && !fuse) {
-        TRY(launch_push(p, PEER_KIND_X, Pn, p->peer_pk[cur ^ 1], stream));
-        mark(p, stream, DIBS_PHASE_ALLGATHER);
-    }
     return DIBS_OK;
 }
 
@@ -974,7 +972,6 @@ static int svgd_steps_impl(dibs_plan* p, int32_t t_start, int32_t n_steps, float
     }
     k_set_state<<<1, 1, 0, stream>>>(p->st, key, t_start);
     LAUNCHED();
-    if (p->p2p) TRY(launch_push(p, PEER_KIND_X, p->pk[0], p->peer_pk[0], stream));   // first step's particle rows
     // scores and sub-keys of the first step; later steps get theirs from the previous step's k_opt_update
     TRY(launch_prologue(p, loc0, p->ld, p->M_loc, p->row0, p->st, nullptr, p->cfg.joint ? 3 : 2, p->cfg.joint ? 2u : 1u,
                         p->scores, p->step_keys, stream));
