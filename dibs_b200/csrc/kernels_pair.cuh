@@ -273,29 +273,50 @@ __global__ void __launch_bounds__(256) k_opt_update(UpdateParams p) {
     const float inv_m = 1.0f / (float)p.n_all;
     const size_t plane = (size_t)p.n_rows * D;
     const float* part = p.phi_part + (size_t)m * D;
-    for (int e = tid; e < D; e += blockDim.x) {
-        float sum = 0.0f;
-        for (int s = 0; s < p.n_jsplit; ++s) sum += part[(size_t)s * plane + e];
-        // -(weighted_gradient_ascent + repulsion).mean(axis=0)   (svgd.py:212-216)
-        const float phi = -sum * inv_m;
-        if (p.phi_out) p.phi_out[(size_t)m * p.phi_ld + e] = phi;
-        float x = p.x_cur[(size_t)m * p.ld + e];
-        if (p.x_next) {
-            if (p.optimizer == 1) {
-                // rmsprop(step, gamma=0.9, eps=1e-8): v = v*gamma + g^2*(1-gamma); x -= step*g/sqrt(v+eps)
-                float* vp = p.v + (size_t)m * p.v_ld + e;
-                float v = __fadd_rn(__fmul_rn(*vp, 0.9f), __fmul_rn(__fmul_rn(phi, phi), 0.1f));
-                *vp = v;
-                x = __fsub_rn(x, __fdiv_rn(__fmul_rn(p.stepsize, phi), __fsqrt_rn(__fadd_rn(v, 1e-8f))));
-            } else {
-                x = __fsub_rn(x, __fmul_rn(p.stepsize, phi));   // sgd: x - step * g
-            }
-            p.x_next[(size_t)m * p.next_ld + e] = x;
-            if (p.push.world) peer_store(p.push, (size_t)(p.row0 + m) * p.next_ld + e, x);
+    // four elements per thread per pass and the slice loop unrolled: every global read of a pass is in flight
+    // before the first one is consumed (the kernel is a chain of L2 latencies otherwise)
+    constexpr int UNR = 4;
+    for (int e0 = tid; e0 < D; e0 += UNR * blockDim.x) {
+        float sum[UNR], xv[UNR], vv[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int e = e0 + u * blockDim.x;
+            sum[u] = 0.0f;
+            xv[u] = e < D ? p.x_cur[(size_t)m * p.ld + e] : 0.0f;
+            vv[u] = (e < D && p.x_next && p.optimizer == 1) ? p.v[(size_t)m * p.v_ld + e] : 0.0f;
         }
-        if (p.scores && e < p.dz) {
-            const int i = e / (2 * k), r = e - i * 2 * k, kk = r >> 1;
-            ((r & 1) ? sV : sU)[kk * d + i] = x;
+#pragma unroll 4
+        for (int s = 0; s < p.n_jsplit; ++s) {
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int e = e0 + u * blockDim.x;
+                if (e < D) sum[u] += part[(size_t)s * plane + e];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int e = e0 + u * blockDim.x;
+            if (e >= D) continue;
+            // -(weighted_gradient_ascent + repulsion).mean(axis=0)   (svgd.py:212-216)
+            const float phi = -sum[u] * inv_m;
+            if (p.phi_out) p.phi_out[(size_t)m * p.phi_ld + e] = phi;
+            float x = xv[u];
+            if (p.x_next) {
+                if (p.optimizer == 1) {
+                    // rmsprop(step, gamma=0.9, eps=1e-8): v = v*gamma + g^2*(1-gamma); x -= step*g/sqrt(v+eps)
+                    const float v = __fadd_rn(__fmul_rn(vv[u], 0.9f), __fmul_rn(__fmul_rn(phi, phi), 0.1f));
+                    p.v[(size_t)m * p.v_ld + e] = v;
+                    x = __fsub_rn(x, __fdiv_rn(__fmul_rn(p.stepsize, phi), __fsqrt_rn(__fadd_rn(v, 1e-8f))));
+                } else {
+                    x = __fsub_rn(x, __fmul_rn(p.stepsize, phi));   // sgd: x - step * g
+                }
+                p.x_next[(size_t)m * p.next_ld + e] = x;
+                if (p.push.world) peer_store(p.push, (size_t)(p.row0 + m) * p.next_ld + e, x);
+            }
+            if (p.scores && e < p.dz) {
+                const int i = e / (2 * k), r = e - i * 2 * k, kk = r >> 1;
+                ((r & 1) ? sV : sU)[kk * d + i] = x;
+            }
         }
     }
     if (p.push.world) peer_signal(p.push, gridDim.x);
