@@ -678,12 +678,17 @@ static int launch_acyc(const dibs_plan* p, const Src& s, int which_split, float*
         const int warps = ACYC_WPC;
         size_t smem = acyclic_rows_smem(d, p->k, p->dmax, warps);
         dim3 grid(s.n, acyc_chunks(p));
+        static const int minb = getenv("DIBS_B200_ACYC_MINB") ? atoi(getenv("DIBS_B200_ACYC_MINB")) : 4;
+#define ACYC_GO(DM, MB) { TRY(set_smem(k_acyclic_rows<DM, MB>, smem)); k_acyclic_rows<DM, MB><<<grid, warps * 32, smem, stream>>>(a); }
+#define ACYC_DM(DM) { if (minb >= 6) ACYC_GO(DM, 6) else if (minb == 5) ACYC_GO(DM, 5) else ACYC_GO(DM, 4) }
         switch (p->dmax) {
-            case 8: TRY(set_smem(k_acyclic_rows<8>, smem)); k_acyclic_rows<8><<<grid, warps * 32, smem, stream>>>(a); break;
-            case 16: TRY(set_smem(k_acyclic_rows<16>, smem)); k_acyclic_rows<16><<<grid, warps * 32, smem, stream>>>(a); break;
-            case 20: TRY(set_smem(k_acyclic_rows<20>, smem)); k_acyclic_rows<20><<<grid, warps * 32, smem, stream>>>(a); break;
-            default: TRY(set_smem(k_acyclic_rows<32>, smem)); k_acyclic_rows<32><<<grid, warps * 32, smem, stream>>>(a); break;
+            case 8: ACYC_DM(8) break;
+            case 16: ACYC_DM(16) break;
+            case 20: ACYC_DM(20) break;
+            default: ACYC_DM(32) break;
         }
+#undef ACYC_DM
+#undef ACYC_GO
     } else if (d <= 32) {
         int warps = a.n_samples < 8 ? a.n_samples : 8;
         size_t smem = acyclic_smem(d, p->k, warps);

@@ -282,6 +282,36 @@ def test_step_vs_oracle_n_vars_20(lik, d, m, s):
         assert err <= 4 * gap + 2e-5 * scale + 1e-6, (which, err, gap, scale)
 
 
+@pytest.mark.parametrize("lik,d", [("lingauss", 8), ("bge", 8), ("densenn", 6), ("lingauss", 36)])
+def test_partitionable_prng_steps(lik, d):
+    """jax_threefry_partitionable=True layout (JAX >= 0.5 default): the unpaired draw paths of every kernel, two full
+    steps against the oracle running the same layout."""
+    from dibs_b200.inference import PRNGKey
+    m = 4
+    g = _mid_case(lik, d=d, m=m, s=6, a=4, n_obs=30)
+    model = build_model(g, sample_case=True, prng_partitionable=True)
+    cfg = oracle_config(g, sample_case=True)
+    cfg.partitionable = True
+    st = orc.init_particles(cfg, PRNGKey(11), m, None, np.float32)
+    x, mask = g["x"], np.zeros(g["x"].shape, np.int32)
+    t = 7
+    ref = st
+    for i in range(2):
+        ref = orc.svgd_step(cfg, ref, t + i, x, mask, np.float32)
+    zeros_t = None if st.theta is None else np.zeros_like(st.theta)
+    z, th, vz, vth, key, sf = model._svgd_loop(t, 2, (st.z, st.theta, np.zeros_like(st.z), zeros_t, st.key,
+                                                      np.zeros(m, np.float32)))
+    assert (np.asarray(key) == ref.key).all()
+    # Two RMSprop steps move every entry by ~stepsize = 5e-3 per step, so a wrong bit stream shows up as O(1e-2)
+    # differences everywhere; the fp32 estimator noise of this small, peaked case (S = 6) is ~1e-5 (the legacy layout
+    # gives the same figure) -- compare robustly.
+    diff = np.abs(npy(z) - ref.z)
+    assert np.median(diff) < 5e-5 and (diff < 1e-3).mean() > 0.97, (np.median(diff), diff.max())
+    if th is not None:
+        dth = np.abs(npy(th) - ref.theta)
+        assert np.median(dth) < 5e-5 and (dth < 1e-3).mean() > 0.97, (np.median(dth), dth.max())
+
+
 def test_properties_full_size():
     """Size-independent properties at BASELINE configs[1] shapes (n_vars=20, n_particles=256, n_mc=64)."""
     from dibs_b200.inference import PRNGKey
