@@ -348,7 +348,6 @@ __global__ void __launch_bounds__(256) k_assemble_grad(AsmParams p) {
             float num = 0.0f;
             for (int c = 0; c < p.th_chunks; ++c) num = fmaf(ta[(size_t)c * p.th_dim + e], sWt[c], num);
             gth[e] = num;
-            if (p.push.world) peer_store(p.push, (size_t)(p.m_offset + m) * p.gth_ld + 2 * d * k + e, num);
         }
     }
     __syncthreads();
@@ -368,10 +367,6 @@ __global__ void __launch_bounds__(256) k_assemble_grad(AsmParams p) {
             dv -= sZ[2 * e + 1] / p.sigma_z2;
         }
         gz[2 * e] = du; gz[2 * e + 1] = dv;
-        if (p.push.world) {
-            const size_t off = (size_t)(p.m_offset + m) * p.gz_ld + 2 * e;
-            peer_store(p.push, off, du); peer_store(p.push, off + 1, dv);
-        }
     }
     if (p.zacc && p.baselines_out && tid == 0) {
         const float b_in = p.baselines_in ? p.baselines_in[m] : 0.0f;
@@ -379,7 +374,20 @@ __global__ void __launch_bounds__(256) k_assemble_grad(AsmParams p) {
         p.baselines_out[m] = (p.z_mode == MC_Z_SCORE)
             ? p.sf_coef * (sMisc[0] / (float)p.n_samples) + (1.0f - p.sf_coef) * b_in : b_in;
     }
-    if (p.push.world) peer_signal(p.push, gridDim.x);
+    if (p.push.world) {
+        // fused exchange: the finished gradient row [dZ | dTheta] (just written, L1/L2-hot) goes to the same row of
+        // every peer's buffer as 128-bit stores (rows are 16-byte aligned, stride a multiple of 4 floats)
+        __syncthreads();
+        const size_t row4 = (size_t)(p.m_offset + m) * p.gz_ld / 4;
+        const float4* src = reinterpret_cast<const float4*>(gz);
+        for (int e = tid; e < p.gz_ld / 4; e += blockDim.x) {
+            const float4 v = __ldcg(src + e);
+#pragma unroll 1
+            for (int q = 0; q < p.push.world; ++q)
+                if (q != p.push.rank) reinterpret_cast<float4*>(p.push.dst[q])[row4 + e] = v;
+        }
+        peer_signal(p.push, gridDim.x);
+    }
 }
 
 inline size_t assemble_smem(int d, int k, int z_chunks, int th_chunks) {
