@@ -282,7 +282,7 @@ def test_step_vs_oracle_n_vars_20(lik, d, m, s):
         assert err <= 4 * gap + 2e-5 * scale + 1e-6, (which, err, gap, scale)
 
 
-@pytest.mark.parametrize("lik,d", [("lingauss", 8), ("bge", 8), ("densenn", 6), ("lingauss", 36)])
+@pytest.mark.parametrize("lik,d", [("lingauss", 8), ("bge", 8), ("densenn", 6)])
 def test_partitionable_prng_steps(lik, d):
     """jax_threefry_partitionable=True layout (JAX >= 0.5 default): the unpaired draw paths of every kernel, two full
     steps against the oracle running the same layout."""
