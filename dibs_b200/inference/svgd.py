@@ -5,8 +5,9 @@ Differences a caller can observe, all deliberate:
   * arrays are torch CUDA tensors (the reference returns jax / numpy arrays);
   * plugins are recognised by class (``native_kind``), arbitrary differentiable Python plugins raise
     ``NotImplementedError`` -- native code cannot autodiff them (SURVEY 'Hard parts');
-  * with an initialised ``torch.distributed`` process group, particles are sharded over the ranks
-    (one NCCL all-gather per step inside the native loop); every rank returns the full particle set.
+  * with an initialised ``torch.distributed`` process group, particles are sharded over the ranks (rows exchanged by
+    peer-memory pushes over NVLink inside the native loop, NCCL all-gathers as the fallback); every rank returns
+    the full particle set, bit-identical to a single-GPU run.
 """
 import numpy as np
 import torch
@@ -134,6 +135,11 @@ class _SVGDBase(DiBS):
         return g_final
 
 
+def _log_normalise(logp):
+    logp = logp.to(torch.float32)
+    return logp - torch.logsumexp(logp, dim=0)
+
+
 class MarginalDiBS(_SVGDBase):
     """SVGD inference of the marginal DAG posterior p(G | D) (reference: dibs/inference/svgd.py:17-375).
 
@@ -161,6 +167,22 @@ class MarginalDiBS(_SVGDBase):
 
     def _parallel_update_z(self, z, kxx_unused, z_all, grad_log_prob_z):
         return self._parallel_update(z_all, None, grad_log_prob_z, None)[0]
+
+    def get_empirical(self, g):
+        """Empirical particle distribution: unique graphs weighted by their counts (svgd.py:333-351)."""
+        from ..metrics import ParticleDistribution
+        g_np = g.detach().cpu().numpy() if hasattr(g, "detach") else np.asarray(g)
+        unique, counts = np.unique(g_np, axis=0, return_counts=True)
+        logp = np.log(counts) - np.log(g_np.shape[0])
+        return ParticleDistribution(logp=torch.from_numpy(logp.astype(np.float32)), g=torch.from_numpy(unique))
+
+    def get_mixture(self, g):
+        """Mixture particle distribution: graphs weighted by the unnormalised posterior log p(D | G) (svgd.py:353-375);
+        the scores come from the native BGe scorer (one launch over all graphs)."""
+        from ..metrics import ParticleDistribution
+        gt = torch.as_tensor(g, device=self.device)
+        logp = self.eltwise_log_joint_prob(gt.to(torch.float32), None)
+        return ParticleDistribution(logp=_log_normalise(logp), g=gt)
 
     def sample(self, *, key, n_particles, steps, n_dim_particles=None, callback=None, callback_every=None):
         """SVGD with DiBS: ``n_particles`` samples G ~ p(G | D); returns int32 [n_particles, d, d] (svgd.py:274-331)."""
@@ -200,6 +222,21 @@ class JointDiBS(_SVGDBase):
     def _parallel_update_theta(self, z_unused, theta_unused, kxx_unused, z_all, theta_all, grad_log_prob_theta):
         zero = torch.zeros_like(self._f32(z_all))
         return self._parallel_update(z_all, theta_all, zero, grad_log_prob_theta)[1]
+
+    def get_empirical(self, g, theta):
+        """Empirical particle distribution; every (G, Theta) particle is unique, weight 1/N each (svgd.py:798-817)."""
+        from ..metrics import ParticleDistribution
+        n = g.shape[0]
+        logp = torch.full((n,), -float(np.log(n)), dtype=torch.float32)
+        return ParticleDistribution(logp=logp, g=g, theta=theta)
+
+    def get_mixture(self, g, theta):
+        """Mixture particle distribution: particles weighted by log p(Theta, D | G) (svgd.py:819-844); scored natively,
+        particle i against its own Theta_i (each graph is passed twice so the launch takes the paired-sample path)."""
+        from ..metrics import ParticleDistribution
+        gt = torch.as_tensor(g, device=self.device).to(torch.float32)
+        logp = self.eltwise_log_joint_prob(torch.stack([gt, gt], dim=1), theta)[:, 0]
+        return ParticleDistribution(logp=_log_normalise(logp), g=torch.as_tensor(g, device=self.device), theta=theta)
 
     def sample(self, *, key, n_particles, steps, n_dim_particles=None, callback=None, callback_every=None):
         """SVGD with DiBS: samples (G, Theta) ~ p(G, Theta | D); returns (int32 [M, d, d], theta pytree) (svgd.py:730-795)."""
