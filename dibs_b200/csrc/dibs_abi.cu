@@ -194,8 +194,14 @@ constexpr int ACYC_WPC = 4;      // warps (= sample pairs) per CTA of the row-pe
 static bool acyc_rows_path(const dibs_plan* p) {
     return p->d <= 32 && (p->cfg.n_acyclicity_mc_samples % 2) == 0 && !p->cfg.prng_partitionable && !getenv("DIBS_B200_OLD_ACYCLIC");
 }
+// experiment switch (default off): run the 4 x 4 register-tile kernel for n_vars <= 32 as well (one warp per sample)
+static bool acyc_tile_small() {
+    static const bool on = getenv("DIBS_B200_ACYC_TILE") && getenv("DIBS_B200_ACYC_TILE")[0] == '1';
+    return on;
+}
 static int acyc_chunks(const dibs_plan* p) {
-    if (p->d > 32 && p->d <= 64) return acyc_dense4_shape(p->d, p->cfg.n_acyclicity_mc_samples).chunks;
+    if ((p->d > 32 && p->d <= 64) || (p->d <= 32 && acyc_tile_small()))
+        return acyc_dense4_shape(p->d, p->cfg.n_acyclicity_mc_samples).chunks;
     if (p->d > 32) return acyc_dense_shape(p->d, p->cfg.n_acyclicity_mc_samples).chunks;
     return acyc_rows_path(p) ? ceil_div(p->cfg.n_acyclicity_mc_samples / 2, ACYC_WPC) : 1;
 }
@@ -673,7 +679,11 @@ static int launch_acyc(const dibs_plan* p, const Src& s, int which_split, float*
     a.keys_override = pass_keys(s, which_split); a.t_override = s.t;
     a.alpha_linear = p->cfg.alpha_linear; a.tau = p->cfg.tau; a.ds_out = ds_out;
     const int d = p->d;
-    if (acyc_rows_path(p)) {
+    if (d <= 32 && acyc_tile_small()) {
+        const AcycDenseShape sh = acyc_dense4_shape(d, a.n_samples);
+        TRY(set_smem(k_acyclic_dense4, sh.smem));
+        k_acyclic_dense4<<<dim3(s.n, sh.chunks), sh.threads, sh.smem, stream>>>(a, sh.ld, sh.nt, sh.rounds);
+    } else if (acyc_rows_path(p)) {
         // row-per-lane kernel: a warp per sample pair (both lanes of each threefry block are used)
         const int warps = ACYC_WPC;
         size_t smem = acyclic_rows_smem(d, p->k, p->dmax, warps);
