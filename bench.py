@@ -66,6 +66,34 @@ def er_edges(d):
     return 2 if d > 5 else 1
 
 
+def simt_peaks():
+    """fp32 / fp64 SIMT FMA peaks in TFLOP/s: measured on this pool's B200 with tools/ubench.cu
+    (profiles/r01/ubench_pipes.json: FFMA2 74.2, DFMA 37.1), else the theoretical 148 SM x 128 lanes x 2 x 1.965 GHz."""
+    p = os.path.join(ROOT, "profiles", "r01", "ubench_pipes.json")
+    try:
+        j = json.load(open(p))
+        return max(float(j["ffma_rrr_tflops"]), float(j.get("ffma2_tflops", 0.0))), float(j["dfma_tflops"]), \
+            "measured (tools/ubench.cu -> profiles/r01/ubench_pipes.json)"
+    except Exception:
+        return FP32_SIMT_TFLOPS, FP32_SIMT_TFLOPS / 2, "theoretical SIMT FMA peak (148 SM x 128 lanes x 2 x 1.965 GHz)"
+
+
+def step_bound(work, kernels, hbm_gbs, fp32_tf, fp64_tf):
+    """t_bound = sum over the kernels of the step of max(bytes / BW_HBM, flops / peak_pipe); returns the
+    bound in microseconds and, per kernel, which side binds.  Only kernels that actually ran (``kernels``) count."""
+    total, per = 0.0, {}
+    for name in kernels:
+        w = work.get(name)
+        if not w or w.get("bound") in ("nvlink", "latency"):
+            continue
+        peak = fp64_tf if w["bound"] == "fp64" else fp32_tf
+        t_mem = w["bytes"] / (hbm_gbs * 1e9) * 1e6
+        t_alu = w["flops"] / (peak * 1e12) * 1e6
+        per[name] = {"us": round(max(t_mem, t_alu), 3), "side": "hbm" if t_mem >= t_alu else "alu"}
+        total += max(t_mem, t_alu)
+    return total, per
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -420,17 +448,29 @@ def run_native(args):
             # the dominant kernels are fp32 (fp64 for BGe) SIMT arithmetic: neither the HBM nor the tensor-pipe roofline
             # bounds them, so the denominator is the fp32 FMA pipe, which MEASURED_PEAKS.json
             # does not carry -> theoretical 148 SM x 128 lanes x 2 x 1.965 GHz (fp64: half of that)
-            peak = FP32_SIMT_TFLOPS * (0.5 if e["bound"] == "fp64" else 1.0)
+            fp32_tf, fp64_tf, simt_src = simt_peaks()
+            peak = fp64_tf if e["bound"] == "fp64" else fp32_tf
             roofline = {"bound": e["bound"] + "_simt", "achieved": e["tflops"], "peak": round(peak, 2), "unit": "TFLOP/s",
                         "frac": round(e["tflops"] / peak, 4), "traffic": traffic,
-                        "peak_source": "theoretical SIMT FMA peak (not in MEASURED_PEAKS.json)",
+                        "peak_source": simt_src + "; MEASURED_PEAKS.json carries no SIMT figure",
                         "hbm_frac_of_measured": round(e["gbs"] / hbm_peak, 5)}
         roofline["kernel"] = dom
         roofline["us_per_launch"] = e["us"]
+        try:
+            # whole-step bound of SURVEY 8(d) next to the measured step (charged with the REFERENCE's algorithm)
+            fp32_tf, fp64_tf, _ = simt_peaks()
+            tb, per = step_bound(work, kernels, hbm_peak, fp32_tf, fp64_tf)
+            roofline["step_bound_us"] = round(tb, 2)
+            roofline["step_frac"] = round(tb / (total_ms / K * 1e3), 4)
+            roofline["step_bound_by_kernel"] = per
+        except Exception:
+            pass
 
     # ---- end to end through the public API with host buffers -------------------------------------------------
     def e2e_once(n_steps):
-        barrier()
+        import gc
+        gc.collect()                                                # plans of earlier models (model <-> plan cycles) go now,
+        barrier()                                                   # not inside the timed region
         t0 = time.perf_counter()
         mdl = build_model(name, x_host, device)                     # H2D of x from pinned host memory
         out = mdl.sample(key=PRNGKey(0), n_particles=m, steps=n_steps)

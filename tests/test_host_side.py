@@ -110,3 +110,31 @@ def test_held_out_scores_and_particle_distributions():
     assert np.allclose(np.exp(mix.logp.numpy()).sum(), 1.0) and np.allclose(mix.logp.numpy(), np.log(0.25))
     mix_j = JointDiBS.get_mixture(Stub(), g, torch.zeros(4, 4))
     assert mix_j.logp.shape == (4,) and np.allclose(np.exp(mix_j.logp.numpy()).sum(), 1.0)
+
+
+def test_bench_work_model_covers_every_phase():
+    """bench.py's per-kernel work formulas name every phase the native timer reports, and the
+    whole-step bound of SURVEY 8(d) is finite and positive for every workload."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from dibs_b200 import _native as nat
+    for name, (_, lik, d, m, s, a, h) in bench.WORKLOADS.items():
+        for world in (1, 8):
+            if m % world:
+                continue
+            work = bench.kernel_work(name, m // world, m)
+            joint = lik != "bge"
+            for ph in nat.PHASES:
+                if ph == "mc_theta" and not joint:
+                    continue
+                assert ph in work, (name, ph)
+                assert work[ph]["bytes"] >= 0 and work[ph]["flops"] >= 0
+            fp32_tf, fp64_tf, _ = bench.simt_peaks()
+            tb, per = bench.step_bound(work, [p for p in work], 6454.6, fp32_tf, fp64_tf)
+            assert np.isfinite(tb) and tb > 0 and "allgather" not in per
+        cfg = bench.config_dict(name, 8 if m % 8 == 0 else 1)
+        assert cfg["workload"].startswith(name) and cfg["particles_per_gpu"] * (8 if m % 8 == 0 else 1) == m
