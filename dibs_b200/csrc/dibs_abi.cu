@@ -682,7 +682,9 @@ static int launch_acyc(const dibs_plan* p, const Src& s, int which_split, float*
     if (d <= 32 && acyc_tile_small()) {
         const AcycDenseShape sh = acyc_dense4_shape(d, a.n_samples);
         TRY(set_smem(k_acyclic_dense4, sh.smem));
-        k_acyclic_dense4<<<dim3(s.n, sh.chunks), sh.threads, sh.smem, stream>>>(a, sh.ld, sh.nt, sh.rounds);
+        const int paired = (!a.partitionable && (a.n_samples % 2) == 0 && (sh.rounds % 2) == 0 &&
+                            sh.chunks * sh.rounds == a.n_samples) ? 1 : 0;
+        k_acyclic_dense4<<<dim3(s.n, sh.chunks), sh.threads, sh.smem, stream>>>(a, sh.ld, sh.nt, sh.rounds, paired);
     } else if (acyc_rows_path(p)) {
         // row-per-lane kernel: a warp per sample pair (both lanes of each threefry block are used)
         const int warps = ACYC_WPC;
@@ -709,7 +711,7 @@ static int launch_acyc(const dibs_plan* p, const Src& s, int which_split, float*
         // 4 x 4 register tiles: one sample per CTA at a time, several CTAs per SM
         const AcycDenseShape sh = acyc_dense4_shape(d, a.n_samples);
         TRY(set_smem(k_acyclic_dense4, sh.smem));
-        k_acyclic_dense4<<<dim3(s.n, sh.chunks), sh.threads, sh.smem, stream>>>(a, sh.ld, sh.nt, sh.rounds);
+        k_acyclic_dense4<<<dim3(s.n, sh.chunks), sh.threads, sh.smem, stream>>>(a, sh.ld, sh.nt, sh.rounds, 0);
     } else {
         // register-tiled matrix powers on shared-memory operands (kernels_dense.cuh)
         const AcycDenseShape sh = acyc_dense_shape(d, a.n_samples);

@@ -262,11 +262,11 @@ static inline AcycDenseShape acyc_dense4_shape(int d, int n_samples) {
     s.threads = ((s.nt + 31) / 32) * 32;
     s.rounds = (n_samples + 7) / 8;                      // <= 8 chunks per particle, fixed decomposition
     s.chunks = (n_samples + s.rounds - 1) / s.rounds;
-    s.smem = 4 * mat + (size_t)d * d * sizeof(float) + 64;
+    s.smem = 4 * mat + (size_t)(d <= 32 ? 2 : 1) * d * d * sizeof(float) + 64;   // sS (+ the paired second graph, n_vars <= 32 only)
     return s;
 }
 
-__global__ void __launch_bounds__(256, 2) k_acyclic_dense4(AcycParams p, int LD, int NT, int rounds) {
+__global__ void __launch_bounds__(256, 2) k_acyclic_dense4(AcycParams p, int LD, int NT, int rounds, int paired) {
     extern __shared__ __align__(16) float smem[];
     const int d = p.d, dd = d * d, TQ = LD / 4;
     const int m = blockIdx.x, tid = threadIdx.x;
@@ -298,12 +298,36 @@ __global__ void __launch_bounds__(256, 2) k_acyclic_dense4(AcycParams p, int LD,
 #pragma unroll
     for (int a = 0; a < 4; ++a) { acc.c[a][0] = 0ull; acc.c[a][1] = 0ull; }
 
+    // `paired` (legacy threefry layout, A and rounds even): the CTA owns the sample PAIRS (q, q + A/2), q in
+    // [blockIdx.y * rounds/2, ...): both lanes of every threefry block are used, the second graph waits in sG2
+    float* sG2 = sRt + MAT;                              // [dd] raw entries of the pair's second graph (paired only)
+    const uint32_t half = n_total >> 1;
     for (int r = 0; r < rounds; ++r) {
-        const int a = blockIdx.y * rounds + r;
-        if (a >= p.n_samples) break;                    // CTA-uniform
+        int a;
+        if (paired) {
+            const int q = blockIdx.y * (rounds >> 1) + (r >> 1);
+            if (q >= (p.n_samples >> 1)) break;          // CTA-uniform
+            a = q + (r & 1) * (p.n_samples >> 1);
+        } else {
+            a = blockIdx.y * rounds + r;
+            if (a >= p.n_samples) break;                 // CTA-uniform
+        }
         for (int i = tid / d, j = tid - (tid / d) * d, e = tid; e < dd; e += blockDim.x) {
             float g = 0.0f;
-            if (i != j) {
+            if (paired) {
+                if ((r & 1) == 0) {
+                    float g1 = 0.0f;
+                    if (i != j) {
+                        const uint32_t e0 = (uint32_t)a * dd + e;
+                        const uint2 bits = threefry2x32(key.x, key.y, e0, e0 + half);
+                        g = entry_from_bits<false>(bits.x, sS[e], fast_soft, p.tau);
+                        g1 = entry_from_bits<false>(bits.y, sS[e], fast_soft, p.tau);
+                    }
+                    sG2[e] = g1;
+                } else {
+                    g = sG2[e];
+                }
+            } else if (i != j) {
                 const uint32_t bits = jax_bits(key, (uint32_t)a * dd + e, n_total, p.partitionable);
                 g = entry_from_bits<false>(bits, sS[e], fast_soft, p.tau);
             }
