@@ -4,7 +4,8 @@
 TAG=${1:-r02}
 OUT=gpurun_out; mkdir -p $OUT
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee $OUT/pytest_gpu_$TAG.txt
-# (1) 4x4-tile acyclicity kernel at n_vars <= 32 (one warp per sample, ~60 registers) vs the row-per-lane kernel
+# (1) 4x4-tile acyclicity kernel at n_vars <= 32 (one warp per sample, ~60 registers) vs the row-per-lane kernel;
+#     parity of the variant was confirmed at the end of round 1 (profiles/r01/pytest_gpu_final.txt), only timing is open
 for v in 0 1; do
   DIBS_B200_ACYC_TILE=$v timeout 300 python bench.py --steps 200 --warmup 10 --no-cpu-baseline 2>/dev/null > $OUT/bench_c2_${TAG}_tile$v.json
   DIBS_B200_ACYC_TILE=$v timeout 300 python -m pytest tests -m gpu -x -q -k "oracle_n_vars_20 or full_steps" 2>&1 | tail -2
