@@ -191,6 +191,20 @@ static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // CTAs per particle of the acyclicity pass (a function of (A, d, PRNG layout) only)
 constexpr int ACYC_WPC = 4;      // warps (= sample pairs) per CTA of the row-per-lane kernel
+
+// tuning knobs for sweeps without a rebuild (defaults = the values the shapes were measured with):
+//   DIBS_B200_MC_CTAS_PER_SM   target CTAs per SM of a Monte-Carlo pass (scales the number of sample chunks)
+//   DIBS_B200_PHI_CTAS         target CTA count of the phi pass (scales the number of j slices)
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    if (!e || !*e) return dflt;
+    const int v = atoi(e);
+    return v > 0 ? v : dflt;
+}
+static int mc_target_ctas(int dflt_per_sm) {
+    static const int per_sm = env_int("DIBS_B200_MC_CTAS_PER_SM", 0);
+    return (per_sm > 0 ? per_sm : dflt_per_sm) * 148;
+}
 static bool acyc_rows_path(const dibs_plan* p) {
     return p->d <= 32 && (p->cfg.n_acyclicity_mc_samples % 2) == 0 && !p->cfg.prng_partitionable && !getenv("DIBS_B200_OLD_ACYCLIC");
 }
@@ -237,7 +251,7 @@ static McShape mc_shape_for(bool qr, int likelihood, int d, int hidden, int n_lo
         sh.gpb = best;
         sh.threads = ((best * d) + 31) / 32 * 32;
         const int rounds = ceil_div(Q, best);
-        int chunks = ceil_div(8 * 148, n_local);
+        int chunks = ceil_div(mc_target_ctas(8), n_local);
         if (chunks > rounds) chunks = rounds;
         if (chunks < 1) chunks = 1;
         const int rpc = ceil_div(rounds, chunks);
@@ -250,7 +264,7 @@ static McShape mc_shape_for(bool qr, int likelihood, int d, int hidden, int n_lo
         sh.paired = pair_ok && (S % 2) == 0;
         const int per = sh.paired ? 2 : 1;
         const int Q = sh.paired ? S / 2 : S;
-        int want = ceil_div(2 * 148, n_local);
+        int want = ceil_div(mc_target_ctas(2), n_local);
         if (want > Q) want = Q;
         if (want < 1) want = 1;
         int spc = ceil_div(Q, want);
@@ -266,7 +280,7 @@ static McShape mc_shape_for(bool qr, int likelihood, int d, int hidden, int n_lo
         // one slot (sample pair when the PRNG layout allows, else one sample) at a time per CTA; chunks of slots
         sh.paired = pair_ok && (S % 2) == 0;
         const int Q = sh.paired ? S / 2 : S;
-        int want = ceil_div(4 * 148, n_local);
+        int want = ceil_div(mc_target_ctas(4), n_local);
         if (want > Q) want = Q;
         if (want < 1) want = 1;
         sh.spc = ceil_div(Q, want);
@@ -280,7 +294,7 @@ static McShape mc_shape_for(bool qr, int likelihood, int d, int hidden, int n_lo
     sh.gpb = gpb;
     sh.threads = 256;
     int max_chunks = ceil_div(S, gpb);
-    int want = ceil_div(2 * 148, n_local);
+    int want = ceil_div(mc_target_ctas(2), n_local);
     if (want < 1) want = 1;
     if (want > max_chunks) want = max_chunks;
     sh.spc = ceil_div(ceil_div(S, want), gpb) * gpb;
@@ -292,7 +306,7 @@ static McShape mc_shape_dense(int d, int n_local, int S) {
     McShape sh;
     sh.qr = false; sh.paired = false; sh.dense = true;
     if (n_local < 1) n_local = 1;
-    int want = ceil_div(4 * 148, n_local);
+    int want = ceil_div(mc_target_ctas(4), n_local);
     if (want > S) want = S;
     if (want < 1) want = 1;
     sh.spc = ceil_div(S, want);
@@ -413,7 +427,8 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
     {
         const int col_tiles = ceil_div(p->Dz, PT_C) + ceil_div(p->Dth, PT_C);
         const int row_scale = p->M / 256 > 1 ? p->M / 256 : 1;
-        int ns = ceil_div(592, col_tiles * row_scale);
+        static const int phi_ctas = env_int("DIBS_B200_PHI_CTAS", 592);
+        int ns = ceil_div(phi_ctas, col_tiles * row_scale);
         const int max_ns = p->M / 64 > 1 ? p->M / 64 : 1;
         if (ns > max_ns) ns = max_ns;
         if (ns < 1) ns = 1;
