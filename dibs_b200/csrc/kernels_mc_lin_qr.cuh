@@ -174,6 +174,40 @@ __global__ void __launch_bounds__(192, (DMAX <= 20 ? 2 : 1)) k_mc_lin_qr(McParam
             u0[i] = (i == j) ? 1.0f : -ga * th;
             u1[i] = (i == j) ? 1.0f : -gb * th;
         }
+#ifdef DIBS_QR_FFMA2
+        // experiment (compile with -DDIBS_QR_FFMA2): the two graphs of the slot as one packed pair per row, so each
+        // mat-vec step is ONE FFMA2 with the Rx operand broadcast -- bit-identical results, half the FMA issue slots
+        f32x2 uu[DMAX];
+#pragma unroll
+        for (int i = 0; i < DMAX; ++i) uu[i] = pack2(u0[i], u1[i]);
+        f32x2 ssq2 = 0ull;
+#pragma unroll
+        for (int i = 0; i < DMAX; ++i) {
+            f32x2 a = 0ull;
+#pragma unroll
+            for (int k = i; k < DMAX; ++k) {
+                const float r = R.v[rtri_off<DMAX>(i, k)];
+                a = fma2(pack2(r, r), uu[k], a);
+            }
+            uu[i] = a;
+            ssq2 = fma2(a, a, ssq2);
+        }
+        float ssq0 = lo2(ssq2), ssq1 = hi2(ssq2);
+        if (MODE == MC_THETA_HARD || MODE == MC_Z_REPARAM) {
+#pragma unroll
+            for (int k = DMAX - 1; k >= 0; --k) {
+                f32x2 a = 0ull;
+#pragma unroll
+                for (int i = 0; i <= k; ++i) {
+                    const float r = R.v[rtri_off<DMAX>(i, k)];
+                    a = fma2(pack2(r, r), uu[i], a);
+                }
+                uu[k] = a;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < DMAX; ++i) { u0[i] = lo2(uu[i]); u1[i] = hi2(uu[i]); }
+#else
         // y = Rx u (in place, ascending rows), ssq = |y|^2
         float ssq0 = 0.0f, ssq1 = 0.0f;
 #pragma unroll
@@ -203,6 +237,7 @@ __global__ void __launch_bounds__(192, (DMAX <= 20 ? 2 : 1)) k_mc_lin_qr(McParam
                 u0[k] = a0; u1[k] = a1;
             }
         }
+#endif
         if (v0) {
             const float cst = (float)p.n_obs * p.log2pis2;
             sNode[(2 * slot) * DMAX + j] = prior0 - 0.5f * (cst + ssq0 * inv_s2);
