@@ -869,6 +869,14 @@ static int launch_kmat(dibs_plan* p, const PairParams& q, cudaStream_t stream) {
 }
 
 static int launch_phi(dibs_plan* p, const PairParams& q, cudaStream_t stream) {
+    static const bool big = getenv("DIBS_B200_PHI_TILE") && getenv("DIBS_B200_PHI_TILE")[0] == '1';   // experiment, default off
+    if (big) {
+        dim3 gb(ceil_div(q.dz, PT_C) + ceil_div(q.dth, PT_C), ceil_div(q.n_rows, PB_I), q.n_jsplit);
+        k_phi_partial_big<<<gb, 128, 0, stream>>>(q);
+        LAUNCHED();
+        mark(p, stream, DIBS_PHASE_PHI_UPDATE);
+        return DIBS_OK;
+    }
     dim3 g3(ceil_div(q.dz, PT_C) + ceil_div(q.dth, PT_C), ceil_div(q.n_rows, PT_I), q.n_jsplit);
     k_phi_partial<<<g3, 128, 0, stream>>>(q);
     LAUNCHED();

@@ -247,6 +247,116 @@ __global__ void __launch_bounds__(128) k_phi_partial(PairParams p) {
     }
 }
 
+// ---- pass 3, experiment (DIBS_B200_PHI_TILE=1; default off until timed): 64 rows x 64 columns per CTA, 128 threads x
+// (8 rows x 4 columns).  Per particle j a thread issues six 128-bit loads (K and Kterm for its 8 rows, x_j and g_j for
+// its 4 columns) for 48 packed FP instructions -- twice the arithmetic per shared-memory byte of the 32-row kernel;
+// K tiles are stored once (no duplication), the row weight enters the FFMA2 as a broadcast scalar.
+// Same j slicing and the same per-element accumulation order as k_phi_partial -> bit-identical partial sums.
+constexpr int PB_I = 64;
+constexpr int PB_KP = 68;   // padded stride of the transposed K tiles [j][i]
+
+__global__ void __launch_bounds__(128) k_phi_partial_big(PairParams p) {
+    __shared__ __align__(16) float sK[PT_J * PB_KP];      // K_full[i][j] transposed: [j][i]
+    __shared__ __align__(16) float sKt[PT_J * PB_KP];     // K term (z or theta block)
+    __shared__ __align__(16) float sXj[PT_J * PT_C];
+    __shared__ __align__(16) float sGj[PT_J * PT_C];
+    peer_wait(p.wait_g);
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;      // ty 0..7: rows 8 ty .. 8 ty + 7
+    const int i0 = blockIdx.y * PB_I;
+    const int D = p.dz + p.dth;
+    const int nzt = (p.dz + PT_C - 1) / PT_C;
+    const bool z_block = (int)blockIdx.x < nzt;
+    const int c0 = z_block ? blockIdx.x * PT_C : p.dz + ((int)blockIdx.x - nzt) * PT_C;
+    const int c_end = z_block ? p.dz : D;
+    const float* kterm = z_block ? p.kz : p.kt;
+    const float h = z_block ? p.h_z : p.h_t;
+    const int j_begin = blockIdx.z * p.j_len;
+    const int j_end = min(p.n_all, j_begin + p.j_len);
+
+    f32x2 xi[8][2], drive[8][2], rep[8][2];               // [row][column pair]
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int gi = i0 + ty * 8 + a, gc = c0 + tx * 4 + 2 * b;
+            const float* xr = p.x_all + (size_t)(p.row0 + gi) * p.ld;
+            const float v0 = (gi < p.n_rows && gc < c_end) ? xr[gc] : 0.0f;
+            const float v1 = (gi < p.n_rows && gc + 1 < c_end) ? xr[gc + 1] : 0.0f;
+            xi[a][b] = pack2(v0, v1);
+            drive[a][b] = 0ull; rep[a][b] = 0ull;
+        }
+
+    for (int j0 = j_begin; j0 < j_end; j0 += PT_J) {
+        for (int e = tid; e < PB_I * PT_J; e += 128) {
+            const int i = e / PT_J, j = e % PT_J;
+            const int gi = i0 + i, gj = j0 + j;
+            const bool ok = gi < p.n_rows && gj < j_end;
+            sK[j * PB_KP + i] = ok ? p.kfull[(size_t)gi * p.n_all + gj] : 0.0f;
+            sKt[j * PB_KP + i] = ok ? kterm[(size_t)gi * p.n_all + gj] : 0.0f;
+        }
+        for (int e = tid; e < PT_J * (PT_C / 4); e += 128) {
+            const int j = e / (PT_C / 4), c4 = (e % (PT_C / 4)) * 4;
+            const int gj = j0 + j, gc = c0 + c4;
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
+            if (gj < j_end) {
+                const size_t ox = (size_t)gj * p.ld + gc, og = (size_t)gj * p.g_ld + gc;
+                if (gc + 3 < c_end &&
+                    ((reinterpret_cast<uintptr_t>(p.x_all + ox) | reinterpret_cast<uintptr_t>(p.g_all + og)) & 15) == 0) {
+                    xv = *reinterpret_cast<const float4*>(p.x_all + ox);
+                    gv = *reinterpret_cast<const float4*>(p.g_all + og);
+                } else {
+                    if (gc < c_end) { xv.x = p.x_all[ox]; gv.x = p.g_all[og]; }
+                    if (gc + 1 < c_end) { xv.y = p.x_all[ox + 1]; gv.y = p.g_all[og + 1]; }
+                    if (gc + 2 < c_end) { xv.z = p.x_all[ox + 2]; gv.z = p.g_all[og + 2]; }
+                    if (gc + 3 < c_end) { xv.w = p.x_all[ox + 3]; gv.w = p.g_all[og + 3]; }
+                }
+            }
+            *reinterpret_cast<float4*>(&sXj[j * PT_C + c4]) = xv;
+            *reinterpret_cast<float4*>(&sGj[j * PT_C + c4]) = gv;
+        }
+        __syncthreads();
+        const int nj = min(PT_J, j_end - j0);
+#pragma unroll 2
+        for (int j = 0; j < nj; ++j) {
+            const float4 kfa = *reinterpret_cast<const float4*>(&sK[j * PB_KP + ty * 8]);
+            const float4 kfb = *reinterpret_cast<const float4*>(&sK[j * PB_KP + ty * 8 + 4]);
+            const float4 kta = *reinterpret_cast<const float4*>(&sKt[j * PB_KP + ty * 8]);
+            const float4 ktb = *reinterpret_cast<const float4*>(&sKt[j * PB_KP + ty * 8 + 4]);
+            const ulonglong2 xj = *reinterpret_cast<const ulonglong2*>(&sXj[j * PT_C + tx * 4]);
+            const ulonglong2 gj = *reinterpret_cast<const ulonglong2*>(&sGj[j * PT_C + tx * 4]);
+            const float kf[8] = {kfa.x, kfa.y, kfa.z, kfa.w, kfb.x, kfb.y, kfb.z, kfb.w};
+            const float kt[8] = {kta.x, kta.y, kta.z, kta.w, ktb.x, ktb.y, ktb.z, ktb.w};
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const f32x2 kfa2 = pack2(kf[a], kf[a]), kta2 = pack2(kt[a], kt[a]);
+                drive[a][0] = fma2(kfa2, gj.x, drive[a][0]);
+                drive[a][1] = fma2(kfa2, gj.y, drive[a][1]);
+                rep[a][0] = fma2(kta2, sub2(xj.x, xi[a][0]), rep[a][0]);
+                rep[a][1] = fma2(kta2, sub2(xj.y, xi[a][1]), rep[a][1]);
+            }
+        }
+        __syncthreads();
+    }
+    const float c2 = -2.0f / h;
+    float* part = p.phi_part + (size_t)blockIdx.z * p.n_rows * D;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int gi = i0 + ty * 8 + a, gc = c0 + tx * 4;
+        if (gi >= p.n_rows) continue;
+        float* o = part + (size_t)gi * D + gc;
+        const float v0 = fmaf(c2, lo2(rep[a][0]), lo2(drive[a][0])), v1 = fmaf(c2, hi2(rep[a][0]), hi2(drive[a][0]));
+        const float v2 = fmaf(c2, lo2(rep[a][1]), lo2(drive[a][1])), v3 = fmaf(c2, hi2(rep[a][1]), hi2(drive[a][1]));
+        if (gc + 3 < c_end && ((((size_t)blockIdx.z * p.n_rows + gi) * D + gc) & 3) == 0) {
+            *reinterpret_cast<float4*>(o) = make_float4(v0, v1, v2, v3);
+        } else {
+            if (gc < c_end) o[0] = v0;
+            if (gc + 1 < c_end) o[1] = v1;
+            if (gc + 2 < c_end) o[2] = v2;
+            if (gc + 3 < c_end) o[3] = v3;
+        }
+    }
+}
+
 // ---- pass 4: per particle, sum the j slices in fixed order -> phi, optimizer step, and -- because the whole new
 // latent row is in shared memory at that point -- the NEXT step's raw scores U V^T (the edge-probability pass,
 // dibs.py:179-181; the next step's sub-keys and loop state come from k_assemble_grad).
