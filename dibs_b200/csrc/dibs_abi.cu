@@ -139,6 +139,7 @@ struct dibs_plan {
     // LinearGaussian, observational data, n_vars > 32: dense Rx and Rx^T on the device (kernels_dense.cuh)
     bool use_dense = false;
     float* rx_dense = nullptr;
+    float* dense_scratch = nullptr;    // DIBS_B200_DENSE_V2 experiment: [M_loc][max_chunks][2][d*d]
     // MC workspace
     int max_chunks = 1, th_acc_size = 0;
     float *th_acc = nullptr, *th_stats = nullptr, *z_acc = nullptr, *z_stats = nullptr, *acyc = nullptr;
@@ -302,15 +303,22 @@ static McShape mc_shape_for(bool qr, int likelihood, int d, int hidden, int n_lo
     return sh;
 }
 
-static McShape mc_shape_dense(int d, int n_local, int S) {
+static bool dense_v2() {
+    static const bool on = getenv("DIBS_B200_DENSE_V2") && getenv("DIBS_B200_DENSE_V2")[0] == '1';   // experiment, default off
+    return on;
+}
+
+static McShape mc_shape_dense(int d, int n_local, int S, bool pair_ok = false) {
     McShape sh;
-    sh.qr = false; sh.paired = false; sh.dense = true;
+    sh.qr = false; sh.dense = true;
+    sh.paired = dense_v2() && pair_ok && (S % 2) == 0;
     if (n_local < 1) n_local = 1;
+    const int U = sh.paired ? S / 2 : S;                 // units per particle: samples, or sample pairs (experiment)
     int want = ceil_div(mc_target_ctas(4), n_local);
-    if (want > S) want = S;
+    if (want > U) want = U;
     if (want < 1) want = 1;
-    sh.spc = ceil_div(S, want);
-    sh.chunks = ceil_div(S, sh.spc);
+    sh.spc = ceil_div(U, want);
+    sh.chunks = ceil_div(U, sh.spc);
     sh.gpb = 1;
     sh.threads = ((dense_nt(d) + 31) / 32) * 32;
     return sh;
@@ -469,7 +477,7 @@ extern "C" int dibs_plan_destroy(dibs_plan* p) {
     if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
     for (int i = 0; i < 3; ++i) { if (p->aux[i]) cudaStreamDestroy(p->aux[i]); if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]); }
     for (int i = 0; i < 2; ++i) if (p->ev_fork[i]) cudaEventDestroy(p->ev_fork[i]);
-    void* ptrs[] = {p->rx_dense, p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->gk[0], p->gk[1], p->peer_flags_local, p->peer_epoch, p->peer_counter, p->v, p->base, p->st, p->step_keys, p->scores,
+    void* ptrs[] = {p->dense_scratch, p->rx_dense, p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->gk[0], p->gk[1], p->peer_flags_local, p->peer_epoch, p->peer_counter, p->v, p->base, p->st, p->step_keys, p->scores,
                     p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->dist_part, p->kz, p->kt, p->kfull, p->phi_part};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
@@ -557,6 +565,10 @@ extern "C" int dibs_set_data(dibs_plan* p, const float* x, const int32_t* mask, 
         CU(cudaMemcpyAsync(p->rx_dense, dense.data(), dense.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
         CU(cudaStreamSynchronize(stream));
         p->use_dense = true;
+        if (dense_v2()) {
+            if (p->dense_scratch) { cudaFree(p->dense_scratch); p->dense_scratch = nullptr; }
+            CU(cudaMalloc((void**)&p->dense_scratch, (size_t)p->M_loc * p->max_chunks * 2 * d * d * sizeof(float)));
+        }
     }
     if (p->cfg.likelihood == DIBS_LIK_BGE) TRY(bge_prepare(p->cfg, d, n_obs, p->x, p->mask, bge_mean_obs_host, &p->bge_r,
                                                        &p->bge_table, &p->bge_coef, &p->bge_r_stride, stream, g_last_error));
@@ -570,7 +582,7 @@ extern "C" int dibs_set_data(dibs_plan* p, const float* x, const int32_t* mask, 
 // pass shape for this plan: the QR kernel needs observational data and -- unless the graphs are supplied by the
 // caller (lp_only hook) -- the legacy threefry layout with an even number of samples (two draws per block)
 static McShape mc_shape(const dibs_plan* p, int n_local, int S, bool lp_only) {
-    if (p->use_dense) return mc_shape_dense(p->d, n_local, S);
+    if (p->use_dense) return mc_shape_dense(p->d, n_local, S, !lp_only && !p->cfg.prng_partitionable);
     const bool qr = p->use_qr && (lp_only || (!p->cfg.prng_partitionable && (S % 2) == 0));
     return mc_shape_for(qr, p->cfg.likelihood, p->d, p->cfg.hidden, n_local, S, !lp_only && !p->cfg.prng_partitionable);
 }
@@ -638,6 +650,9 @@ static int launch_mc(const dibs_plan* p, McParams q, const McShape& sh, cudaStre
     size_t smem = 0;
     int e = 0;
     if (sh.dense) {
+        q.dense_v2 = (dense_v2() && p->dense_scratch && q.n_local <= p->M_loc && q.n_chunks <= p->max_chunks) ? 1 : 0;
+        q.dense_scratch = p->dense_scratch;
+        if (!q.dense_v2) q.paired = 0;
         smem = lin_dense_smem(p->d);
         auto kern = k_mc_lin_dense<MODE>;
         TRY(set_smem(kern, smem));

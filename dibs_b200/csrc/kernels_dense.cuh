@@ -445,11 +445,53 @@ __global__ void __launch_bounds__(256, 1) k_mc_lin_dense(McParams p, const float
 
     Tile8 acc; tile_zero(acc);
     float m_run = -INFINITY, l_run = 0.0f, sum_lp = 0.0f;
-    const int s_begin = c * p.s_per_chunk, s_end = min(S, s_begin + p.s_per_chunk);
+    // experiment (DIBS_B200_DENSE_V2=1): sigmoid / exp of the scores once per CTA (per-CTA global scratch, each entry
+    // written and re-read by the same thread), no integer divisions in the draw loop, and -- legacy threefry layout,
+    // even S -- sample PAIRS (q, q + S/2) per CTA so that both lanes of every threefry block are used
+    const bool v2 = p.dense_v2 != 0;
+    const bool paired = v2 && p.paired != 0 && !use_ext;
+    float* sc = v2 ? p.dense_scratch + ((size_t)m * p.n_chunks + c) * 2 * dd : nullptr;
+    if (v2 && !use_ext) {
+        for (int e = tid; e < dd; e += blockDim.x) {
+            const float a = srow ? alpha * srow[e] : 0.0f;
+            sc[e] = HARD ? sigmoidf_ref(a) : (fast_soft ? expf(-a) : a);
+        }
+    }
+    const int n_units = paired ? (S >> 1) : S;
+    const int u_begin = c * p.s_per_chunk, u_end = min(n_units, u_begin + p.s_per_chunk);
+    const int n_it = (u_end - u_begin) * (paired ? 2 : 1);
+    const uint32_t half = n_total >> 1;
     __syncthreads();
 
-    for (int s = s_begin; s < s_end; ++s) {
+    for (int it = 0; it < n_it; ++it) {
+        const int s = paired ? (u_begin + (it >> 1) + (it & 1) * (S >> 1)) : (u_begin + it);
         // ---- draw the graph; U = I - G o Theta
+        if (v2) {
+            for (int i = tid / d, j = tid - (tid / d) * d, e = tid; e < dd; e += blockDim.x) {
+                float g = 0.0f;
+                if (i != j) {
+                    if (use_ext) g = p.g_ext[((size_t)m * S + s) * dd + e];
+                    else if (paired) {
+                        if ((it & 1) == 0) {
+                            const uint32_t e0 = (uint32_t)s * dd + e;
+                            const uint2 bits = threefry2x32(key.x, key.y, e0, e0 + half);
+                            const float sa = sc[e];
+                            g = entry_from_bits<HARD>(bits.x, sa, fast_soft, p.tau);
+                            sc[dd + e] = entry_from_bits<HARD>(bits.y, sa, fast_soft, p.tau);
+                        } else {
+                            g = sc[dd + e];
+                        }
+                    } else {
+                        const uint32_t bits = jax_bits(key, (uint32_t)s * dd + e, n_total, p.partitionable);
+                        g = entry_from_bits<HARD>(bits, sc[e], fast_soft, p.tau);
+                    }
+                }
+                sGm[i * LD + j] = g;
+                sW[i * LD + j] = (i == j ? 1.0f : 0.0f) - g * sTh[i * LD + j];
+                j += blockDim.x;
+                while (j >= d) { j -= d; ++i; }
+            }
+        } else {
         for (int e = tid; e < dd; e += blockDim.x) {
             const int i = e / d, j = e - i * d;
             float g = 0.0f;
@@ -464,6 +506,7 @@ __global__ void __launch_bounds__(256, 1) k_mc_lin_dense(McParams p, const float
             }
             sGm[i * LD + j] = g;
             sW[i * LD + j] = (i == j ? 1.0f : 0.0f) - g * sTh[i * LD + j];
+        }
         }
         __syncthreads();
         // ---- prior column partials of the tile rows: sum_i g logN(theta; mean_edge, sig_edge)  (linearGaussian.py:289)

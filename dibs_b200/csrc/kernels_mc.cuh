@@ -25,7 +25,8 @@ struct McParams {
     int n_particles;                     // M, global
     int d, k, n_obs, n_samples;
     int n_chunks, s_per_chunk, gpb;      // chunking of the MC axis; graphs per block-round
-    int paired;                          // BGe: units are sample pairs (s, s + S/2)
+    int paired;                          // units are sample pairs (s, s + S/2)
+    int dense_v2; float* dense_scratch;  // k_mc_lin_dense experiment: [n_local][n_chunks][2][d*d] per-CTA scratch
     const float* x;                      // [N, d]
     const int32_t* mask;                 // [N, d] or null
     const StepState* st; int which_split; int partitionable;

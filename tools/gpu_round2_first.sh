@@ -15,6 +15,11 @@ DIBS_B200_PHI_TILE=1 timeout 300 python -m pytest tests -m gpu -x -q -k "kernel_
 for wl in c2 t_lin; do for v in 0 1; do
   DIBS_B200_PHI_TILE=$v timeout 300 python bench.py --workload $wl --steps 200 --warmup 10 --no-cpu-baseline 2>/dev/null > $OUT/bench_${wl}_${TAG}_phitile$v.json
 done; done
+# (1c) dense LinearGaussian draw phase V2 (per-CTA precomputed probabilities, no integer divisions, paired threefry lanes)
+DIBS_B200_DENSE_V2=1 timeout 300 python -m pytest tests -m gpu -x -q -k "oracle_n_vars_20 and lingauss" 2>&1 | tail -2
+for v in 0 1; do
+  DIBS_B200_DENSE_V2=$v timeout 300 python bench.py --workload c5 --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null > $OUT/bench_c5_${TAG}_densetile$v.json
+done
 # (2) where the time goes in the BGe and DenseNN passes now
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_mc_bge|k_mc_nn' -s 4 -c 3 -f -o $OUT/prof_bge_$TAG \
     python bench.py --workload t_bge --steps 6 --warmup 3 --no-cpu-baseline > $OUT/ncu_bge_$TAG.log 2>&1
