@@ -12,6 +12,7 @@ LIK = {"bge": 0, "lingauss": 1, "densenn": 2}
 PRIOR = {"er": 0, "sf": 1, "uniform": 2}
 ESTIMATOR = {"score": 0, "reparam": 1}
 OPTIMIZER = {"gd": 0, "rmsprop": 1}
+PEER_MAX = 16          # ranks the peer-memory flag table holds (kernels_peer.cuh)
 
 
 class DibsConfig(ctypes.Structure):
@@ -36,11 +37,13 @@ PROTOTYPES = {
     "dibs_plan_create": (ctypes.c_int, [ctypes.POINTER(DibsConfig), ctypes.POINTER(_P)]),
     "dibs_plan_destroy": (ctypes.c_int, [_P]),
     "dibs_theta_dim": (ctypes.c_int, [_P]),
+    "dibs_plan_status": (ctypes.c_int, [_P]),
     "dibs_set_data": (ctypes.c_int, [_P, _P, _P, _I, _P, _P]),
     "dibs_nccl_unique_id": (ctypes.c_int, [_P]),
     "dibs_plan_attach_nccl": (ctypes.c_int, [_P, _P]),
     "dibs_plan_ipc_export": (ctypes.c_int, [_P, _P]),
     "dibs_plan_ipc_attach": (ctypes.c_int, [_P, _P]),
+    "dibs_plan_ipc_detach": (ctypes.c_int, [_P]),
     "dibs_svgd_steps": (ctypes.c_int, [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "dibs_svgd_steps_timed": (ctypes.c_int, [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, ctypes.c_int64, _P, _P]),
     "dibs_init_particles": (ctypes.c_int, [_P, _P, _P, _P, _P]),
@@ -53,6 +56,7 @@ PROTOTYPES = {
     "dibs_grad_theta_likelihood": (ctypes.c_int, [_P, _P, _P, _I, _P, _I, _P, _P]),
     "dibs_grad_latent_prior": (ctypes.c_int, [_P, _P, _I, _P, _I, _I, _P, _P]),
     "dibs_acyclic_constr": (ctypes.c_int, [_P, _P, _I, _P, _P]),
+    "dibs_particle_summary": (ctypes.c_int, [_P, _P, _I, _I, _P, _P]),
     "dibs_kernel_matrix": (ctypes.c_int, [_P, _P, _P, _I, _P, _P]),
     "dibs_svgd_phi": (ctypes.c_int, [_P, _P, _P, _P, _P, _I, _P, _P, _P]),
     "dibs_prng_split": (ctypes.c_int, [_P, _I, _I, _P]),

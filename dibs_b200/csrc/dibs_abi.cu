@@ -124,6 +124,11 @@ struct dibs_plan {
     uint32_t* peer_epoch = nullptr;         // [PEER_KINDS]
     uint32_t* peer_counter = nullptr;       // [PEER_KINDS]
     bool p2p = false;
+    uint32_t* peer_error = nullptr;         // mapped host word: a bounded peer wait that timed out leaves (kind, rank) here
+    uint32_t* peer_error_dev = nullptr;     // its device alias
+    unsigned long long peer_timeout_ns = 0;
+    float* summary_ws = nullptr; size_t summary_cap = 0;   // dibs_particle_summary scratch
+    bool step_ws = false;                   // the step workspace below is allocated on first use (hook-only plans never need it)
     float* peer_pk[2][PEER_MAX] = {};
     float* peer_gk[2][PEER_MAX] = {};
     uint32_t* peer_flags[PEER_MAX] = {};
@@ -390,32 +395,6 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
     }
     p->th_acc_size = p->Dth;
 
-    auto alloc = [&](void** ptr, size_t bytes) -> int {
-        CU(cudaMalloc(ptr, bytes ? bytes : 4));
-        CU(cudaMemset(*ptr, 0, bytes ? bytes : 4));
-        return DIBS_OK;
-    };
-    int r = DIBS_OK;
-    // buffers that may be shared through CUDA IPC get whole 2 MiB blocks of their own
-    size_t pk_bytes = (((size_t)p->M * p->ld * sizeof(float)) + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
-    if ((r = alloc((void**)&p->pk[0], pk_bytes)) || (r = alloc((void**)&p->pk[1], pk_bytes)) ||
-        (r = alloc((void**)&p->gk[0], pk_bytes)) || (r = alloc((void**)&p->gk[1], pk_bytes)) ||
-        (r = alloc((void**)&p->peer_flags_local, 2u << 20)) ||
-        (r = alloc((void**)&p->peer_epoch, PEER_KINDS * sizeof(uint32_t))) ||
-        (r = alloc((void**)&p->peer_counter, PEER_KINDS * sizeof(uint32_t))) ||
-        (r = alloc((void**)&p->v, (size_t)p->M_loc * p->D * sizeof(float))) ||
-        (r = alloc((void**)&p->base, (size_t)p->M_loc * sizeof(float))) ||
-        (r = alloc((void**)&p->st, 2 * sizeof(StepState))) ||
-        (r = alloc((void**)&p->step_keys, (size_t)3 * p->M_loc * 2 * sizeof(uint32_t))) ||
-        (r = alloc((void**)&p->scores, (size_t)p->M_loc * p->d * p->d * sizeof(float))) ||
-        (r = alloc((void**)&p->z_acc, (size_t)p->M_loc * p->max_chunks * d * d * sizeof(float))) ||
-        (r = alloc((void**)&p->z_stats, (size_t)p->M_loc * p->max_chunks * 4 * sizeof(float))) ||
-        (r = alloc((void**)&p->th_acc, (size_t)p->M_loc * p->max_chunks * p->th_acc_size * sizeof(float))) ||
-        (r = alloc((void**)&p->th_stats, (size_t)p->M_loc * p->max_chunks * 4 * sizeof(float))) ||
-        (r = alloc((void**)&p->acyc, (size_t)p->M_loc * acyc_chunks(p) * d * d * sizeof(float)))) {
-        dibs_plan_destroy(p);
-        return r;
-    }
     // pairwise: split the feature axis until the distance pass has >= ~2 x 148 CTAs; Z and Theta features are cut
     // separately so that a split never straddles the Z | Theta boundary
     {
@@ -443,14 +422,63 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
         p->j_len = ceil_div(ceil_div(p->M, ns), PT_J) * PT_J;
         p->n_jsplit = ceil_div(p->M, p->j_len);
     }
+    *out = p;
+    return DIBS_OK;
+}
+
+// Workspace of the step loop (particle / gradient buffers, Monte-Carlo partials, pairwise planes): allocated by the
+// first dibs_svgd_steps / dibs_plan_ipc_export call, so plans that only serve the per-function hooks stay a few KB.
+static int ensure_step_ws(dibs_plan* p) {
+    if (p->step_ws) return DIBS_OK;
+    const int d = p->d;
+    auto alloc = [&](void** ptr, size_t bytes) -> int {
+        CU(cudaMalloc(ptr, bytes ? bytes : 4));
+        CU(cudaMemset(*ptr, 0, bytes ? bytes : 4));
+        return DIBS_OK;
+    };
+    int r = DIBS_OK;
+    if (!p->peer_error) {
+        CU(cudaHostAlloc((void**)&p->peer_error, sizeof(uint32_t), cudaHostAllocMapped));
+        *p->peer_error = 0u;
+        CU(cudaHostGetDevicePointer((void**)&p->peer_error_dev, p->peer_error, 0));
+        const char* e = getenv("DIBS_B200_PEER_TIMEOUT_MS");
+        p->peer_timeout_ns = (unsigned long long)(e && *e ? atoll(e) : 10000) * 1000000ull;
+    }
+    // buffers that may be shared through CUDA IPC get whole 2 MiB blocks of their own
+    size_t pk_bytes = (((size_t)p->M * p->ld * sizeof(float)) + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+    if ((r = alloc((void**)&p->pk[0], pk_bytes)) || (r = alloc((void**)&p->pk[1], pk_bytes)) ||
+        (r = alloc((void**)&p->gk[0], pk_bytes)) || (r = alloc((void**)&p->gk[1], pk_bytes)) ||
+        (r = alloc((void**)&p->peer_flags_local, 2u << 20)) ||
+        (r = alloc((void**)&p->peer_epoch, PEER_KINDS * sizeof(uint32_t))) ||
+        (r = alloc((void**)&p->peer_counter, PEER_KINDS * sizeof(uint32_t))) ||
+        (r = alloc((void**)&p->v, (size_t)p->M_loc * p->D * sizeof(float))) ||
+        (r = alloc((void**)&p->base, (size_t)p->M_loc * sizeof(float))) ||
+        (r = alloc((void**)&p->st, 2 * sizeof(StepState))) ||
+        (r = alloc((void**)&p->step_keys, (size_t)3 * p->M_loc * 2 * sizeof(uint32_t))) ||
+        (r = alloc((void**)&p->scores, (size_t)p->M_loc * p->d * p->d * sizeof(float))) ||
+        (r = alloc((void**)&p->z_acc, (size_t)p->M_loc * p->max_chunks * d * d * sizeof(float))) ||
+        (r = alloc((void**)&p->z_stats, (size_t)p->M_loc * p->max_chunks * 4 * sizeof(float))) ||
+        (r = alloc((void**)&p->th_acc, (size_t)p->M_loc * p->max_chunks * p->th_acc_size * sizeof(float))) ||
+        (r = alloc((void**)&p->th_stats, (size_t)p->M_loc * p->max_chunks * 4 * sizeof(float))) ||
+        (r = alloc((void**)&p->acyc, (size_t)p->M_loc * acyc_chunks(p) * d * d * sizeof(float))))
+        return r;
     size_t plane = (size_t)p->M_loc * p->M * sizeof(float);
     if ((r = alloc((void**)&p->dist_part, plane * p->n_split)) || (r = alloc((void**)&p->kz, plane)) ||
         (r = alloc((void**)&p->kt, plane)) || (r = alloc((void**)&p->kfull, plane)) ||
-        (r = alloc((void**)&p->phi_part, (size_t)p->n_jsplit * p->M_loc * p->D * sizeof(float)))) {
-        dibs_plan_destroy(p);
+        (r = alloc((void**)&p->phi_part, (size_t)p->n_jsplit * p->M_loc * p->D * sizeof(float))))
         return r;
+    p->step_ws = true;
+    return DIBS_OK;
+}
+
+extern "C" int dibs_plan_status(dibs_plan* p) {
+    if (!p) return fail(DIBS_ERR_INVALID_ARG, "null plan");
+    if (p->peer_error && *(volatile uint32_t*)p->peer_error) {
+        const uint32_t w = *(volatile uint32_t*)p->peer_error;
+        static const char* kinds[] = {"gradient rows", "particle rows", "call-done flag", "sync flag"};
+        return fail(DIBS_ERR_STATE, std::string("peer-memory exchange timed out waiting for the ") + kinds[(w >> 8) & 3] +
+                                        " of rank " + std::to_string(w & 0xff) + " (a peer died or the ranks ran different step counts)");
     }
-    *out = p;
     return DIBS_OK;
 }
 
@@ -477,7 +505,8 @@ extern "C" int dibs_plan_destroy(dibs_plan* p) {
     if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
     for (int i = 0; i < 3; ++i) { if (p->aux[i]) cudaStreamDestroy(p->aux[i]); if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]); }
     for (int i = 0; i < 2; ++i) if (p->ev_fork[i]) cudaEventDestroy(p->ev_fork[i]);
-    void* ptrs[] = {p->dense_scratch, p->rx_dense, p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->gk[0], p->gk[1], p->peer_flags_local, p->peer_epoch, p->peer_counter, p->v, p->base, p->st, p->step_keys, p->scores,
+    if (p->peer_error) cudaFreeHost(p->peer_error);
+    void* ptrs[] = {p->summary_ws, p->dense_scratch, p->rx_dense, p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->gk[0], p->gk[1], p->peer_flags_local, p->peer_epoch, p->peer_counter, p->v, p->base, p->st, p->step_keys, p->scores,
                     p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->dist_part, p->kz, p->kt, p->kfull, p->phi_part};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
@@ -936,6 +965,7 @@ static int launch_push(dibs_plan* p, int kind, const float* local, float* const*
 static PeerWait make_wait(const dibs_plan* p, int kind) {
     PeerWait w;
     w.flags = p->p2p ? p->peer_flags_local : nullptr; w.epoch = p->peer_epoch; w.world = p->cfg.world_size; w.kind = kind;
+    w.error = p->peer_error_dev; w.timeout_ns = p->peer_timeout_ns;
     return w;
 }
 
@@ -999,6 +1029,12 @@ __global__ void k_set_state(StepState* st, const uint32_t* key, int t) {
     st->key[0] = key[0]; st->key[1] = key[1]; st->t = t; st->pad = 0;
 }
 __global__ void k_get_key(const StepState* st, uint32_t* key) { key[0] = st->key[0]; key[1] = st->key[1]; }
+// per-kernel timing mode: hold the stream for `ns` so that the host has enqueued the whole eager step before its first
+// kernel starts -- the event-to-event times are then kernel durations, not host launch gaps
+__global__ void k_delay(unsigned long long ns) {
+    const unsigned long long t0 = global_timer_ns();
+    while (global_timer_ns() - t0 < ns) __nanosleep(200);
+}
 
 static int svgd_steps_impl(dibs_plan* p, int32_t t_start, int32_t n_steps, float* z, float* theta, float* v_z,
                            float* v_theta, uint32_t* key, float* sf_baseline, void* stream_, bool timed, int per_kernel,
@@ -1009,6 +1045,8 @@ static int svgd_steps_impl(dibs_plan* p, int32_t t_start, int32_t n_steps, float
     const bool rms = p->cfg.optimizer == DIBS_OPT_RMSPROP;
     if (rms && (!v_z || (p->Dth && !v_theta))) return fail(DIBS_ERR_INVALID_ARG, "rmsprop needs v_z / v_theta");
     if (n_steps <= 0) return DIBS_OK;
+    TRY(dibs_plan_status(p));
+    TRY(ensure_step_ws(p));
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t fz = sizeof(float) * p->Dz, ft = sizeof(float) * p->Dth, fl = sizeof(float) * p->ld, fd = sizeof(float) * p->D;
     float* loc0 = p->pk[0] + (size_t)p->row0 * p->ld;
@@ -1075,6 +1113,7 @@ static int svgd_steps_impl(dibs_plan* p, int32_t t_start, int32_t n_steps, float
                     NC(g_nccl.AllGather(p->peer_epoch, p->peer_flags_local, 1, 7, p->comm, stream));
                 }
             }
+            if (per_kernel) { k_delay<<<1, 1, 0, stream>>>(300000ull); LAUNCHED(); }
             p->timing = true;
             mark(p, stream, -1);
             p->timing = per_kernel != 0;
@@ -1162,6 +1201,7 @@ static const int IPC_BUFS = 5;   // pk[0], pk[1], gk[0], gk[1], flags
 extern "C" int dibs_plan_ipc_export(dibs_plan* p, uint8_t* handles_out) {
     if (!p || !handles_out) return fail(DIBS_ERR_INVALID_ARG, "null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    TRY(ensure_step_ws(p));
     void* bufs[IPC_BUFS] = {p->pk[0], p->pk[1], p->gk[0], p->gk[1], p->peer_flags_local};
     for (int i = 0; i < IPC_BUFS; ++i) {
         cudaIpcMemHandle_t h;
@@ -1170,6 +1210,8 @@ extern "C" int dibs_plan_ipc_export(dibs_plan* p, uint8_t* handles_out) {
     }
     return DIBS_OK;
 }
+
+extern "C" int dibs_plan_ipc_detach(dibs_plan* p);
 
 extern "C" int dibs_plan_ipc_attach(dibs_plan* p, const uint8_t* all_handles) {
     if (!p || !all_handles) return fail(DIBS_ERR_INVALID_ARG, "null argument");
@@ -1184,7 +1226,12 @@ extern "C" int dibs_plan_ipc_attach(dibs_plan* p, const uint8_t* all_handles) {
             for (int i = 0; i < IPC_BUFS; ++i) {
                 cudaIpcMemHandle_t h;
                 memcpy(&h, all_handles + ((size_t)q * IPC_BUFS + i) * 64, 64);
-                CU(cudaIpcOpenMemHandle(&opened[i], h, cudaIpcMemLazyEnablePeerAccess));
+                cudaError_t e = cudaIpcOpenMemHandle(&opened[i], h, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) {
+                    cudaGetLastError();
+                    dibs_plan_ipc_detach(p);
+                    return fail(DIBS_ERR_CUDA, std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(q) + "): " + cudaGetErrorString(e));
+                }
                 p->ipc_opened.push_back(opened[i]);
             }
         }
@@ -1194,6 +1241,22 @@ extern "C" int dibs_plan_ipc_attach(dibs_plan* p, const uint8_t* all_handles) {
     }
     for (int i = 0; i < 2; ++i) if (p->gexec[i]) { cudaGraphExecDestroy(p->gexec[i]); p->gexec[i] = nullptr; }
     p->p2p = true;
+    return DIBS_OK;
+}
+
+extern "C" int dibs_plan_ipc_detach(dibs_plan* p) {
+    if (!p) return fail(DIBS_ERR_INVALID_ARG, "null argument");
+    if (!p->ipc_opened.empty()) {
+        cudaDeviceSynchronize();
+        for (void* q : p->ipc_opened) cudaIpcCloseMemHandle(q);
+        p->ipc_opened.clear();
+    }
+    for (int q = 0; q < PEER_MAX; ++q) {
+        p->peer_pk[0][q] = p->peer_pk[1][q] = p->peer_gk[0][q] = p->peer_gk[1][q] = nullptr;
+        p->peer_flags[q] = nullptr;
+    }
+    for (int i = 0; i < 2; ++i) if (p->gexec[i]) { cudaGraphExecDestroy(p->gexec[i]); p->gexec[i] = nullptr; }
+    p->p2p = false;
     return DIBS_OK;
 }
 
@@ -1371,6 +1434,28 @@ extern "C" int dibs_acyclic_constr(dibs_plan* p, const float* g, int32_t n, floa
     TRY(set_smem(k_acyclic_value, smem));
     k_acyclic_value<<<n, 256, smem, (cudaStream_t)stream_>>>(g, n, p->d, h_out);
     LAUNCHED();
+    return DIBS_OK;
+}
+
+extern "C" int dibs_particle_summary(dibs_plan* p, const float* z, int32_t n, int32_t t, float* summary_host, void* stream_) {
+    if (!p || !z || !summary_host || n < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_particle_summary: bad arguments");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int d = p->d, dd = d * d;
+    const size_t need = (size_t)n * dd + n + 2 + dd;
+    if (p->summary_cap < need) {
+        // growing the scratch is the only synchronising path (first call / larger particle set)
+        if (p->summary_ws) { CU(cudaStreamSynchronize(stream)); CU(cudaFree(p->summary_ws)); p->summary_ws = nullptr; }
+        CU(cudaMalloc((void**)&p->summary_ws, need * sizeof(float)));
+        p->summary_cap = need;
+    }
+    float* p_all = p->summary_ws; float* h_all = p_all + (size_t)n * dd; float* rec = h_all + n;
+    const size_t smem = ((size_t)4 * d * (d | 1) + 2 * (size_t)d * p->k) * sizeof(float);
+    TRY(set_smem(k_particle_summary, smem));
+    k_particle_summary<<<n, 256, smem, stream>>>(z, p->Dz, n, d, p->k, p->cfg.alpha_linear * (float)t, p_all, h_all);
+    LAUNCHED();
+    k_summary_reduce<<<ceil_div(dd, 256), 256, 0, stream>>>(p_all, h_all, n, dd, rec);
+    LAUNCHED();
+    CU(cudaMemcpyAsync(summary_host, rec, (size_t)(2 + dd) * sizeof(float), cudaMemcpyDeviceToHost, stream));
     return DIBS_OK;
 }
 

@@ -32,7 +32,15 @@ struct PeerWait {
     const uint32_t* flags;           // local flag array [PEER_KINDS][PEER_MAX], or null (single GPU / NCCL path)
     const uint32_t* epoch;           // [PEER_KINDS]
     int world, kind;
+    uint32_t* error;                 // plan-level error word (mapped host memory): set when a wait times out
+    unsigned long long timeout_ns;   // bound of one wait (0: wait forever)
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
@@ -44,12 +52,25 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
 }
 
 // every CTA of a consumer calls this first: wait until all ranks' rows of the current epoch have landed
+// The spin is BOUNDED: a rank that died or fell out of sequence must not hang every GPU of the node.  After
+// timeout_ns the waiter records (kind, missing rank) in the plan's error word and carries on with whatever rows it
+// has; the host turns a non-zero error word into DIBS_ERR_STATE at the next call / dibs_plan_status().
 __device__ __forceinline__ void peer_wait(const PeerWait& w) {
     if (w.flags == nullptr) return;
     if ((int)threadIdx.x < w.world) {
         const uint32_t want = w.epoch[w.kind];
         const uint32_t* f = w.flags + w.kind * PEER_MAX + threadIdx.x;
-        while ((int32_t)(ld_acquire_sys(f) - want) < 0) { __nanosleep(20); }
+        if ((int32_t)(ld_acquire_sys(f) - want) < 0) {
+            const unsigned long long t0 = global_timer_ns();
+            unsigned spins = 0;
+            while ((int32_t)(ld_acquire_sys(f) - want) < 0) {
+                __nanosleep(20);
+                if (w.timeout_ns && (++spins & 1023u) == 0 && global_timer_ns() - t0 > w.timeout_ns) {
+                    if (w.error) *(volatile uint32_t*)w.error = 0x80000000u | ((uint32_t)w.kind << 8) | threadIdx.x;   // benign race: any writer will do
+                    break;
+                }
+            }
+        }
     }
     __syncthreads();
 }

@@ -203,6 +203,71 @@ __global__ void __launch_bounds__(256) k_acyclic_value(const float* g, int n, in
 }
 
 // ------------------------------------------------------------------------------------------
+// progress summary of a particle set for the callback path (dibs.py:661-692: the reference's visualize_callback
+// computes particle_to_g_lim, edge_probs and `(elwise_acyclic_constr_nograd(gs) > 0).sum()` on the host side of a
+// blocking transfer).  Here: one CTA per particle -> edge probabilities, G_lim, h(G_lim) with the same power loop
+// as k_acyclic_value; a second kernel reduces over particles in fixed order into [#cyclic, n, mean edge probs];
+// the caller copies that record to pinned host memory asynchronously -- the step stream never waits for the host.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_particle_summary(const float* z, int z_ld, int n, int d, int k, float alpha,
+                                                          float* p_out, float* h_out) {
+    extern __shared__ __align__(16) float smem[];
+    const int ld = d | 1, mat = d * ld, tid = threadIdx.x;
+    float* bZ0 = smem; float* bZ1 = smem + mat; float* bR0 = smem + 2 * mat; float* bR1 = smem + 3 * mat;
+    float* sZ = smem + 4 * mat;                       // [2*d*k]
+    const float* zrow = z + (size_t)blockIdx.x * z_ld;
+    for (int e = tid; e < 2 * d * k; e += blockDim.x) sZ[e] = zrow[e];
+    __syncthreads();
+    const float inv_d = 1.0f / (float)d;
+    for (int e = tid; e < d * d; e += blockDim.x) {
+        const int i = e / d, j = e % d;
+        float acc = 0.0f;
+        for (int kk = 0; kk < k; ++kk) acc = fmaf(sZ[(i * k + kk) * 2], sZ[(j * k + kk) * 2 + 1], acc);
+        p_out[(size_t)blockIdx.x * d * d + e] = (i == j) ? 0.0f : sigmoidf_ref(alpha * acc);
+        const float g = (i != j && acc > 0.0f) ? 1.0f : 0.0f;                // particle_to_g_lim (dibs.py:84-99)
+        bZ0[i * ld + j] = (i == j ? 1.0f : 0.0f) + inv_d * g;
+    }
+    __syncthreads();
+    float* zc = bZ0; float* zn = bZ1; float* rc = nullptr; float* rn = bR0;
+    int nn = d;
+    while (nn > 0) {
+        if (nn & 1) {
+            if (rc == nullptr) { for (int e = tid; e < mat; e += blockDim.x) rn[e] = zc[e]; }
+            else group_matmul(rc, zc, rn, d, ld, tid, blockDim.x);
+            float* tmp = rc; rc = rn; rn = (tmp == nullptr) ? bR1 : tmp;
+            __syncthreads();
+        }
+        nn >>= 1;
+        if (nn > 0) {
+            group_matmul(zc, zc, zn, d, ld, tid, blockDim.x);
+            float* tmp = zc; zc = zn; zn = tmp;
+            __syncthreads();
+        }
+    }
+    if (tid < 32) {
+        float tr = 0.0f;
+        for (int i = tid; i < d; i += 32) tr += rc[i * ld + i];
+        tr = warp_sum(tr);
+        if (tid == 0) h_out[blockIdx.x] = tr - (float)d;
+    }
+}
+
+// out[0] = #particles with h(G_lim) > 0, out[1] = n, out[2 + e] = mean over particles of edge_probs[e]
+__global__ void __launch_bounds__(256) k_summary_reduce(const float* p_all, const float* h_all, int n, int dd, float* out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < dd) {
+        float s = 0.0f;
+        for (int m = 0; m < n; ++m) s += p_all[(size_t)m * dd + e];
+        out[2 + e] = s / (float)n;
+    }
+    if (e == 0) {
+        int c = 0;
+        for (int m = 0; m < n; ++m) c += h_all[m] > 0.0f ? 1 : 0;
+        out[0] = (float)c; out[1] = (float)n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // assemble: partials -> d log p / dZ (and d/dTheta) for one particle
 // ------------------------------------------------------------------------------------------
 struct AsmParams {

@@ -7,8 +7,9 @@ Python/PyTorch implementation of the math and no fallback.  Arrays are torch CUD
   z       float32 [..., d, k, 2]      theta   the likelihood model's pytree (or its flat [M, Dtheta] form)
   keys    uint32 bit patterns [.., 2] (any integer dtype / numpy / torch accepted)
 """
+import collections
 import ctypes
-
+import hashlib
 import os
 
 import numpy as np
@@ -50,6 +51,35 @@ def keys_from_device(t):
     return t.detach().cpu().numpy().view(np.uint32).copy()
 
 
+# Process-level cache of native plans.  A plan owns the workspace, the data-dependent precomputation (QR factor of x,
+# BGe statistics), the captured CUDA graphs of the step and -- on several GPUs -- the opened CUDA-IPC peer buffers;
+# none of that depends on WHICH model object asks, only on the POD configuration, the data and the process group.
+# Keying the cache on exactly those lets a new ``JointDiBS(...)`` on the same problem reuse all of it (the reference
+# gets the same effect from jit's compilation cache, svgd.py:270).  Least-recently-used plans beyond the bound are
+# destroyed (their device memory is released as soon as no caller still holds them).
+_PLAN_CACHE = collections.OrderedDict()
+_PLAN_CACHE_MAX = max(1, int(os.environ.get("DIBS_B200_PLAN_CACHE", "8")))
+
+
+def clear_plan_cache():
+    """Drop every cached native plan (frees their device memory once unreferenced)."""
+    _PLAN_CACHE.clear()
+
+
+def _digest(*arrays):
+    h = hashlib.sha1()
+    for a in arrays:
+        if a is None:
+            h.update(b"-")
+            continue
+        if isinstance(a, torch.Tensor):
+            a = a.detach().cpu().numpy()
+        a = np.ascontiguousarray(a)
+        h.update(str(a.shape).encode() + str(a.dtype).encode())
+        h.update(a.tobytes())
+    return h.hexdigest()
+
+
 class DiBS:
     """Backbone shared by :class:`MarginalDiBS` and :class:`JointDiBS` (reference: dibs/inference/dibs.py:12-78)."""
 
@@ -59,12 +89,9 @@ class DiBS:
         if not torch.cuda.is_available():
             raise RuntimeError("dibs_b200 needs a CUDA device (sm_100a); there is no CPU path")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.x = torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x).to(self.device, torch.float32).contiguous()
-        if interv_mask is None:
-            self.interv_mask = None
-        else:
-            im = interv_mask if isinstance(interv_mask, torch.Tensor) else torch.as_tensor(np.asarray(interv_mask))
-            self.interv_mask = im.to(self.device, torch.int32).contiguous()
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.x, self.interv_mask, self._data_digest = self._upload_data(x, interv_mask, likelihood_model)
         self.n_vars = self.x.shape[-1]
         self.graph_model = graph_model
         self.likelihood_model = likelihood_model
@@ -91,7 +118,6 @@ class DiBS:
                 raise NotImplementedError(f"{what} {type(obj).__name__} has no native implementation in dibs_b200")
         if hasattr(likelihood_model, "check_native"):
             likelihood_model.check_native()
-        self._plans = {}
 
     # ------------------------------------------------------------------ plan management
     def _dist(self):
@@ -105,13 +131,23 @@ class DiBS:
             return float(self.latent_prior_std)
         return float(np.float32(1.0) / np.sqrt(np.float32(n_dim)))   # svgd.py:142,302 in fp32
 
-    def _plan(self, n_particles, n_dim=None, sharded=False):
-        """Native plan for (M, k); ``sharded`` plans split particles over the torch.distributed ranks."""
-        n_dim = n_dim or self.n_vars
-        world, rank = self._dist() if sharded else (1, 0)
-        k = (int(n_particles), int(n_dim), world, rank)
-        if k in self._plans:
-            return self._plans[k]
+    def _upload_data(self, x, interv_mask, likelihood_model):
+        """-> (x float32 [N, d] on the device, mask int32 [N, d] or None, digest of the data a plan precomputes from)."""
+        xh = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))
+        xd = xh.to(self.device, torch.float32, non_blocking=True).contiguous()
+        md, mh = None, None
+        if interv_mask is not None:
+            mh = interv_mask if isinstance(interv_mask, torch.Tensor) else torch.as_tensor(np.asarray(interv_mask))
+            md = mh.to(self.device, torch.int32, non_blocking=True).contiguous()
+        mean_obs = getattr(likelihood_model, "mean_obs", None)
+        return xd, md, _digest(xh, mh, None if mean_obs is None else np.asarray(mean_obs, np.float32))
+
+    def _call(self, fn, *args):
+        """One native call with this model's device current (plans allocate and launch on the current device)."""
+        with torch.cuda.device(self.device):
+            nat.check(getattr(nat.lib(), fn)(*args))
+
+    def _config(self, n_particles, n_dim, world, rank):
         if self.grad_estimator_z not in nat.ESTIMATOR:
             raise ValueError(f'Unknown gradient estimator `{self.grad_estimator_z}`')     # dibs.py:318
         lm, gm = self.likelihood_model, self.graph_model
@@ -144,17 +180,35 @@ class DiBS:
         c.bge_alpha_mu = getattr(lm, "alpha_mu", 1.0)
         c.bge_alpha_lambd = getattr(lm, "alpha_lambd", self.n_vars + 2)
         c.world_size, c.rank = world, rank
+        return c
+
+    def _plan(self, n_particles, n_dim=None, sharded=False, data=None):
+        """Native plan for (M, k); ``sharded`` plans split particles over the torch.distributed ranks.  ``data`` =
+        (x, mask, digest) scores against another data set (held-out likelihoods); default: the model's own."""
+        n_dim = n_dim or self.n_vars
+        world, rank = self._dist() if sharded else (1, 0)
+        c = self._config(int(n_particles), int(n_dim), world, rank)
+        x, mask, digest = data or (self.x, self.interv_mask, self._data_digest)
+        group = None
+        if world > 1:
+            import torch.distributed as dist
+            group = id(dist.distributed_c10d._get_default_group())
+        key = (bytes(c), digest, self.device.index, group)
+        plan = _PLAN_CACHE.get(key)
+        if plan is not None:
+            _PLAN_CACHE.move_to_end(key)
+            return plan
         handle = ctypes.c_void_p()
-        nat.check(nat.lib().dibs_plan_create(ctypes.byref(c), ctypes.byref(handle)))
-        plan = _Plan(handle, c, self)
-        mean_obs = getattr(lm, "mean_obs", None)
+        self._call("dibs_plan_create", ctypes.byref(c), ctypes.byref(handle))
+        plan = _Plan(handle, c, self.device)
+        mean_obs = getattr(self.likelihood_model, "mean_obs", None)
         mean_np = None if mean_obs is None else np.ascontiguousarray(np.asarray(mean_obs, np.float32))
-        with torch.cuda.device(self.device):
-            nat.check(nat.lib().dibs_set_data(handle, nat.ptr(self.x), nat.ptr(self.interv_mask), self.x.shape[0],
-                                              nat.ptr(mean_np), self._stream()))
+        self._call("dibs_set_data", handle, nat.ptr(x), nat.ptr(mask), x.shape[0], nat.ptr(mean_np), self._stream())
         if world > 1:
             plan.attach_nccl()
-        self._plans[k] = plan
+        _PLAN_CACHE[key] = plan
+        while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
+            _PLAN_CACHE.popitem(last=False)          # least recently used; destroyed when unreferenced
         return plan
 
     def _stream(self):
@@ -181,7 +235,7 @@ class DiBS:
         n = int(np.prod(lead)) if lead else 1
         out = torch.empty((n, d, d), dtype=torch.int32, device=self.device)
         plan = self._plan(max(n, 1), k)
-        nat.check(nat.lib().dibs_particle_to_g_lim(plan.handle, nat.ptr(z), n, nat.ptr(out), self._stream()))
+        self._call("dibs_particle_to_g_lim", plan.handle, nat.ptr(z), n, nat.ptr(out), self._stream())
         return out.reshape(*lead, d, d)
 
     def edge_probs(self, z, t):
@@ -191,7 +245,7 @@ class DiBS:
         n = int(np.prod(lead)) if lead else 1
         out = torch.empty((n, d, d), dtype=torch.float32, device=self.device)
         plan = self._plan(max(n, 1), k)
-        nat.check(nat.lib().dibs_edge_probs(plan.handle, nat.ptr(z), n, int(t), nat.ptr(out), self._stream()))
+        self._call("dibs_edge_probs", plan.handle, nat.ptr(z), n, int(t), nat.ptr(out), self._stream())
         return out.reshape(*lead, d, d)
 
     def sample_g(self, p, subk, n_samples):
@@ -203,8 +257,8 @@ class DiBS:
         keys = keys_to_device(np.asarray(as_key(subk)).reshape(n, 2), self.device)
         out = torch.empty((n, n_samples, self.n_vars, self.n_vars), dtype=torch.int32, device=self.device)
         plan = self._plan(n)
-        nat.check(nat.lib().dibs_sample_graphs(plan.handle, nat.ptr(p), nat.ptr(keys), n, int(n_samples), nat.ptr(out),
-                                               self._stream()))
+        self._call("dibs_sample_graphs", plan.handle, nat.ptr(p), nat.ptr(keys), n, int(n_samples), nat.ptr(out),
+                                               self._stream())
         return out[0] if single else out
 
     def sample_soft_g(self, z, subk, n_samples, t):
@@ -216,8 +270,8 @@ class DiBS:
         keys = keys_to_device(np.asarray(as_key(subk)).reshape(n, 2), self.device)
         out = torch.empty((n, n_samples, d, d), dtype=torch.float32, device=self.device)
         plan = self._plan(n, k)
-        nat.check(nat.lib().dibs_soft_graphs(plan.handle, nat.ptr(z), nat.ptr(keys), n, int(n_samples), int(t), nat.ptr(out),
-                                             self._stream()))
+        self._call("dibs_soft_graphs", plan.handle, nat.ptr(z), nat.ptr(keys), n, int(n_samples), int(t), nat.ptr(out),
+                                             self._stream())
         return out[0] if single else out
 
     # ------------------------------------------------------------------ likelihood estimators (dibs.py:255-551)
@@ -235,8 +289,8 @@ class DiBS:
             theta = self._flat_theta(theta)
         out = torch.empty((n, s), dtype=torch.float32, device=self.device)
         plan = self._plan(n)
-        nat.check(nat.lib().dibs_log_joint_prob(plan.handle, nat.ptr(gs.contiguous()), nat.ptr(theta), n, s, nat.ptr(out),
-                                                self._stream()))
+        self._call("dibs_log_joint_prob", plan.handle, nat.ptr(gs.contiguous()), nat.ptr(theta), n, s, nat.ptr(out),
+                                                self._stream())
         return out[0] if single else out
 
     def eltwise_grad_z_likelihood(self, zs, thetas, baselines, t, subkeys):
@@ -251,8 +305,8 @@ class DiBS:
         grad = torch.empty_like(zs)
         base_out = torch.empty_like(base)
         plan = self._plan(n, k)
-        nat.check(nat.lib().dibs_grad_z_likelihood(plan.handle, nat.ptr(zs), nat.ptr(theta), nat.ptr(base), int(t),
-                                                   nat.ptr(keys), n, nat.ptr(grad), nat.ptr(base_out), self._stream()))
+        self._call("dibs_grad_z_likelihood", plan.handle, nat.ptr(zs), nat.ptr(theta), nat.ptr(base), int(t),
+                                                   nat.ptr(keys), n, nat.ptr(grad), nat.ptr(base_out), self._stream())
         return grad, base_out
 
     def eltwise_grad_theta_likelihood(self, zs, thetas, t, subkeys):
@@ -263,8 +317,8 @@ class DiBS:
         keys = keys_to_device(np.asarray(as_key(subkeys)).reshape(n, 2), self.device)
         grad = torch.empty_like(theta)
         plan = self._plan(n, k)
-        nat.check(nat.lib().dibs_grad_theta_likelihood(plan.handle, nat.ptr(zs), nat.ptr(theta), int(t), nat.ptr(keys), n,
-                                                       nat.ptr(grad), self._stream()))
+        self._call("dibs_grad_theta_likelihood", plan.handle, nat.ptr(zs), nat.ptr(theta), int(t), nat.ptr(keys), n,
+                                                       nat.ptr(grad), self._stream())
         return grad
 
     # ------------------------------------------------------------------ latent prior (dibs.py:557-658)
@@ -275,8 +329,8 @@ class DiBS:
         keys = keys_to_device(np.asarray(as_key(subkeys)).reshape(n, 2), self.device)
         grad = torch.empty_like(zs)
         plan = self._plan(n, k)
-        nat.check(nat.lib().dibs_grad_latent_prior(plan.handle, nat.ptr(zs), int(t), nat.ptr(keys), n, int(constraint_only),
-                                                   nat.ptr(grad), self._stream()))
+        self._call("dibs_grad_latent_prior", plan.handle, nat.ptr(zs), int(t), nat.ptr(keys), n, int(constraint_only),
+                                                   nat.ptr(grad), self._stream())
         return grad
 
     def grad_constraint_gumbel(self, single_z, key, t):
@@ -291,17 +345,43 @@ class DiBS:
         g = g.reshape(-1, self.n_vars, self.n_vars)
         out = torch.empty((g.shape[0],), dtype=torch.float32, device=self.device)
         plan = self._plan(g.shape[0])
-        nat.check(nat.lib().dibs_acyclic_constr(plan.handle, nat.ptr(g), g.shape[0], nat.ptr(out), self._stream()))
+        self._call("dibs_acyclic_constr", plan.handle, nat.ptr(g), g.shape[0], nat.ptr(out), self._stream())
         return out[0] if single else out
 
+    def particle_summary(self, zs, t):
+        """Enqueue the device-side progress summary of a particle set (``dibs_particle_summary``): returns
+        (record, event) where ``record`` is a pinned host tensor [2 + d*d] = (#cyclic, n, mean edge probabilities) that
+        is valid once ``event`` has completed.  Nothing here waits for the GPU."""
+        zs = self._f32(zs)
+        n, k = zs.shape[0], zs.shape[2]
+        rec = torch.empty(2 + self.n_vars * self.n_vars, dtype=torch.float32, pin_memory=True)
+        plan = self._plan(n, k)
+        self._call("dibs_particle_summary", plan.handle, nat.ptr(zs), n, int(t), nat.ptr(rec), self._stream())
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return rec, ev, zs                      # zs kept alive until the kernels have run
+
+    def _flush_summary(self):
+        pend, self._pending_summary = self._pending_summary, None
+        if pend is None:
+            return
+        t, (rec, ev, _) = pend
+        ev.synchronize()                        # enqueued a whole chunk ago: complete unless the chunk was tiny
+        self.last_summary = dict(t=t, n_cyclic=int(rec[0].item()), n_particles=int(rec[1].item()),
+                                 edge_marginals=rec[2:].reshape(self.n_vars, self.n_vars).clone())
+        print(f'iteration {t:6d} | alpha {self.alpha(t):6.1f} | beta {self.beta(t):6.1f} '
+              f'| #cyclic {self.last_summary["n_cyclic"]:3d}')
+
     def visualize_callback(self, ipython=True, save_path=None):
-        """Text-only progress callback (the reference plots with matplotlib, dibs.py:661-692: out of scope)."""
+        """Progress callback (dibs.py:661-692), text only -- the reference's matplotlib grid is out of scope.  The
+        summary (#cyclic graphs among G_lim, mean edge probabilities) is computed on the device and streamed to pinned
+        host memory; a callback prints the PREVIOUS chunk's line, so it never blocks on the chunk it was called for
+        (``sample()`` flushes the last line when the loop ends; also available as ``self.last_summary``)."""
+        self._pending_summary = None
+
         def callback(**kwargs):
-            zs = kwargs["zs"]
-            gs = self.particle_to_g_lim(zs)
-            n_cyclic = int((self.acyclic_constr(gs.to(torch.float32)) > 0).sum().item())
-            print(f'iteration {kwargs["t"]:6d} | alpha {self.alpha(kwargs["t"]):6.1f} | beta {self.beta(kwargs["t"]):6.1f} '
-                  f'| #cyclic {n_cyclic:3d}')
+            self._flush_summary()
+            self._pending_summary = (kwargs["t"], self.particle_summary(kwargs["zs"], kwargs["t"]))
         return callback
 
 
@@ -316,55 +396,69 @@ def _add_leading(theta):
 
 
 class _Plan:
-    """Owns one native ``dibs_plan``."""
+    """Owns one native ``dibs_plan`` (shared between model objects through the process-level cache)."""
 
-    def __init__(self, handle, cfg, owner):
-        self.handle, self.cfg, self.owner = handle, cfg, owner
+    def __init__(self, handle, cfg, device):
+        self.handle, self.cfg, self.device = handle, cfg, device
         self.n_local = cfg.n_particles // cfg.world_size
         self.row0 = cfg.rank * self.n_local
         self.theta_dim = nat.lib().dibs_theta_dim(handle)
+        self.exchange = "none"
+
+    def check(self):
+        """Raise if a bounded peer wait of the exchange timed out (``dibs_plan_status``)."""
+        nat.check(nat.lib().dibs_plan_status(self.handle))
 
     def attach_nccl(self):
-        """Two communicators: the gradient exchange (critical path) and the particle exchange (side branch of the
-        step graph) -- independent communicators, so the two may run in either order on different ranks."""
+        """Multi-GPU exchange set-up, once per plan: peer-memory pushes over NVLink (CUDA IPC) when every rank can open
+        every peer's buffers, else two NCCL communicators -- the gradient exchange (critical path) and the particle
+        exchange (side branch of the step graph), independent so the two may run in either order on different ranks."""
         if os.environ.get("DIBS_B200_NO_P2P") != "1" and self._attach_peer_memory():
+            self.exchange = "peer-memory"
             return                      # rows travel by peer-memory pushes: no communicator needed
         self._attach_one()
         self._attach_one()
+        self.exchange = "nccl"
+
+    def _agree(self, ok, device):
+        """MIN over the ranks of a local success flag (every rank takes the same branch afterwards)."""
+        import torch.distributed as dist
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return int(flag.item()) == 1
 
     def _attach_peer_memory(self):
         """Exchange CUDA-IPC handles of the plan's particle / gradient / flag buffers and open the peers' copies: the
-        step then pushes rows over NVLink peer memory instead of calling NCCL (kernels_peer.cuh).  All ranks take
-        the same branch: the outcome of the local attach is agreed on with an all-reduce."""
+        step then pushes rows over NVLink peer memory instead of calling NCCL (kernels_peer.cuh).  Returns False --
+        on EVERY rank, with nothing left open -- when any rank cannot export or attach (ranks on different nodes, more
+        ranks than the flag table holds, no P2P between two devices); the caller then falls back to NCCL."""
         import torch.distributed as dist
-        dev = self.owner.device
+        dev = self.device
         world = self.cfg.world_size
+        if world > nat.PEER_MAX:
+            return False                # same on every rank: no collective needed to agree
         mine = np.zeros(320, np.uint8)
-        ok = 1
         with torch.cuda.device(dev):
-            if nat.lib().dibs_plan_ipc_export(self.handle, nat.ptr(mine)) != 0:
-                ok = 0
+            ok = nat.lib().dibs_plan_ipc_export(self.handle, nat.ptr(mine)) == 0
         on_gpu = dist.get_backend() == "nccl"
-        blob = torch.from_numpy(mine).to(dev) if on_gpu else torch.from_numpy(mine)
-        allb = torch.empty(world * 320, dtype=torch.uint8, device=blob.device)
+        cdev = dev if on_gpu else torch.device("cpu")
+        blob = torch.from_numpy(mine).to(cdev)
+        allb = torch.empty(world * 320, dtype=torch.uint8, device=cdev)
         dist.all_gather_into_tensor(allb, blob)
-        flag = torch.tensor([ok], dtype=torch.int32, device=blob.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) != 1:
+        if not self._agree(ok, cdev):
             return False
         buf = np.ascontiguousarray(allb.cpu().numpy())
         with torch.cuda.device(dev):
-            ok = 1 if nat.lib().dibs_plan_ipc_attach(self.handle, nat.ptr(buf)) == 0 else 0
-        flag = torch.tensor([ok], dtype=torch.int32, device=blob.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)       # also the barrier: every rank has opened its peers
-        if int(flag.item()) != 1:
-            raise RuntimeError("dibs_b200: CUDA IPC attach succeeded on some ranks only: " +
-                               nat.lib().dibs_last_error().decode())
+            ok = nat.lib().dibs_plan_ipc_attach(self.handle, nat.ptr(buf)) == 0
+        if not self._agree(ok, cdev):   # also the barrier: every rank has opened its peers
+            with torch.cuda.device(dev):
+                nat.lib().dibs_plan_ipc_detach(self.handle)     # close what this rank opened; back to the NCCL path
+            return False
         return True
 
     def _attach_one(self):
         import torch.distributed as dist
-        dev = self.owner.device
+        dev = self.device
         ident = torch.zeros(128, dtype=torch.uint8)
         if self.cfg.rank == 0:
             buf = np.zeros(128, np.uint8)
@@ -380,7 +474,8 @@ class _Plan:
     def __del__(self):
         try:
             if self.handle:
-                nat.lib().dibs_plan_destroy(self.handle)
+                with torch.cuda.device(self.device):
+                    nat.lib().dibs_plan_destroy(self.handle)
                 self.handle = None
         except Exception:
             pass

@@ -30,8 +30,7 @@ class _SVGDBase(DiBS):
         if self._joint:
             theta = torch.empty((n_particles, plan.theta_dim), dtype=torch.float32, device=self.device)
         kdev = keys_to_device(key, self.device)
-        with torch.cuda.device(self.device):
-            nat.check(nat.lib().dibs_init_particles(plan.handle, nat.ptr(kdev), nat.ptr(z), nat.ptr(theta), self._stream()))
+        self._call("dibs_init_particles", plan.handle, nat.ptr(kdev), nat.ptr(z), nat.ptr(theta), self._stream())
         return (z, theta) if self._joint else z
 
     def _f_kernel_mat(self, x_latents, x_thetas=None):
@@ -41,8 +40,8 @@ class _SVGDBase(DiBS):
         theta = self._flat_theta(x_thetas) if self._joint else None
         out = torch.empty((n, n), dtype=torch.float32, device=self.device)
         plan = self._plan(n, k)
-        nat.check(nat.lib().dibs_kernel_matrix(plan.handle, nat.ptr(z.reshape(n, -1)), nat.ptr(theta), n, nat.ptr(out),
-                                               self._stream()))
+        self._call("dibs_kernel_matrix", plan.handle, nat.ptr(z.reshape(n, -1)), nat.ptr(theta), n, nat.ptr(out),
+                                               self._stream())
         return out
 
     def _parallel_update(self, z, theta, grad_z, grad_theta):
@@ -55,8 +54,8 @@ class _SVGDBase(DiBS):
         phi_z = torch.empty_like(z)
         phi_th = torch.empty_like(th) if self._joint else None
         plan = self._plan(n, k)
-        nat.check(nat.lib().dibs_svgd_phi(plan.handle, nat.ptr(z.reshape(n, -1)), nat.ptr(th), nat.ptr(gz.reshape(n, -1)),
-                                          nat.ptr(gth), n, nat.ptr(phi_z), nat.ptr(phi_th), self._stream()))
+        self._call("dibs_svgd_phi", plan.handle, nat.ptr(z.reshape(n, -1)), nat.ptr(th), nat.ptr(gz.reshape(n, -1)),
+                                          nat.ptr(gth), n, nat.ptr(phi_z), nat.ptr(phi_th), self._stream())
         return phi_z, phi_th
 
     def _svgd_loop(self, start, n_steps, init):
@@ -74,12 +73,28 @@ class _SVGDBase(DiBS):
         sf = self._f32(sf).clone()
         key_dev = keys_to_device(key, self.device)
         plan = self._plan(m, k)
-        with torch.cuda.device(self.device):
-            nat.check(nat.lib().dibs_svgd_steps(plan.handle, int(start), int(n_steps), nat.ptr(z), nat.ptr(theta),
-                                                nat.ptr(v_z), nat.ptr(v_theta), nat.ptr(key_dev), nat.ptr(sf), self._stream()))
+        self._call("dibs_svgd_steps", plan.handle, int(start), int(n_steps), nat.ptr(z), nat.ptr(theta),
+                   nat.ptr(v_z), nat.ptr(v_theta), nat.ptr(key_dev), nat.ptr(sf), self._stream())
         torch.cuda.synchronize(self.device)
+        plan.check()
         from .dibs import keys_from_device
         return z, theta, v_z, v_theta, keys_from_device(key_dev), sf
+
+    def _score_held_out(self, g, theta, x_ho, interv_msk_ho):
+        """Score n graphs (one per particle) against ANOTHER data set through the native scorer: a plan bound to
+        (x_ho, mask) -- cached like every plan -- and one ``dibs_log_joint_prob`` launch with S = 1."""
+        data = self._upload_data(x_ho, interv_msk_ho, self.likelihood_model)
+        gt = torch.as_tensor(g, device=self.device).to(torch.float32)
+        if gt.dim() == 2:
+            gt = gt[None]
+        n = gt.shape[0]
+        th = self._flat_theta(theta) if self._joint else None
+        reps = 2 if self._joint else 1      # joint scorers draw sample PAIRS: pass each graph twice, keep the first
+        gs = gt[:, None].expand(n, reps, *gt.shape[1:]).contiguous()
+        out = torch.empty((n, reps), dtype=torch.float32, device=self.device)
+        plan = self._plan(n, data=data)
+        self._call("dibs_log_joint_prob", plan.handle, nat.ptr(gs), nat.ptr(th), n, reps, nat.ptr(out), self._stream())
+        return out[:, 0]
 
     def _theta_out(self, flat):
         return self.likelihood_model.unflatten(flat)
@@ -110,16 +125,18 @@ class _SVGDBase(DiBS):
         def gather(local):
             if world == 1:
                 return local
+            if dist.get_backend() != "nccl":            # gloo: collectives on host tensors
+                out = torch.empty((n_particles,) + tuple(local.shape[1:]), dtype=local.dtype)
+                dist.all_gather_into_tensor(out, local.contiguous().cpu())
+                return out.to(local.device)
             out = torch.empty((n_particles,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
             dist.all_gather_into_tensor(out, local.contiguous())
             return out
 
         callback_every = callback_every or steps
         for t in (range(0, steps, callback_every) if steps else range(0)):
-            with torch.cuda.device(self.device):
-                nat.check(nat.lib().dibs_svgd_steps(plan.handle, int(t), int(callback_every), nat.ptr(z), nat.ptr(theta),
-                                                    nat.ptr(v_z), nat.ptr(v_theta), nat.ptr(key_dev), nat.ptr(sf_baseline),
-                                                    self._stream()))
+            self._call("dibs_svgd_steps", plan.handle, int(t), int(callback_every), nat.ptr(z), nat.ptr(theta),
+                       nat.ptr(v_z), nat.ptr(v_theta), nat.ptr(key_dev), nat.ptr(sf_baseline), self._stream())
             if callback:
                 kw = dict(dibs=self, t=t + callback_every, zs=gather(z).clone())
                 if self._joint:
@@ -127,9 +144,14 @@ class _SVGDBase(DiBS):
                 callback(**kw)
 
         z_final = gather(z)
+        if getattr(self, "_pending_summary", None) is not None:
+            self._flush_summary()                              # last progress line of visualize_callback
         self._last_state = dict(z=z_final, theta=gather(theta) if self._joint else None, v_z=v_z, v_theta=v_theta,
                                 key=key_dev, sf_baseline=sf_baseline)
         g_final = self.particle_to_g_lim(z_final)
+        if world > 1:
+            torch.cuda.synchronize(self.device)
+            plan.check()                                       # a timed-out peer wait surfaces here, not as a hang
         if self._joint:
             return g_final, self._theta_out(self._last_state["theta"])
         return g_final
@@ -178,11 +200,19 @@ class MarginalDiBS(_SVGDBase):
 
     def get_mixture(self, g):
         """Mixture particle distribution: graphs weighted by the unnormalised posterior log p(D | G) (svgd.py:353-375);
-        the scores come from the native BGe scorer (one launch over all graphs)."""
+        the scores come from the native BGe scorer, one CTA per graph (n = M particles with one graph each)."""
         from ..metrics import ParticleDistribution
         gt = torch.as_tensor(g, device=self.device)
-        logp = self.eltwise_log_joint_prob(gt.to(torch.float32), None)
+        logp = self.eltwise_log_joint_prob(gt.to(torch.float32)[:, None], None)[:, 0]
         return ParticleDistribution(logp=_log_normalise(logp), g=gt)
+
+    def eltwise_log_marginal_likelihood_observ(self, g, x_ho):
+        """log p(x_ho | G) for a batch of graphs g [n, d, d] on held-out observational data (svgd.py:110-111)."""
+        return self._score_held_out(g, None, x_ho, None)
+
+    def eltwise_log_marginal_likelihood_interv(self, g, x_ho, interv_msk_ho):
+        """log p(x_ho | G) on held-out interventional data with its intervention mask (svgd.py:112-113)."""
+        return self._score_held_out(g, None, x_ho, interv_msk_ho)
 
     def sample(self, *, key, n_particles, steps, n_dim_particles=None, callback=None, callback_every=None):
         """SVGD with DiBS: ``n_particles`` samples G ~ p(G | D); returns int32 [n_particles, d, d] (svgd.py:274-331)."""
@@ -237,6 +267,15 @@ class JointDiBS(_SVGDBase):
         gt = torch.as_tensor(g, device=self.device).to(torch.float32)
         logp = self.eltwise_log_joint_prob(torch.stack([gt, gt], dim=1), theta)[:, 0]
         return ParticleDistribution(logp=_log_normalise(logp), g=torch.as_tensor(g, device=self.device), theta=theta)
+
+    def eltwise_log_likelihood_observ(self, g, theta, x_ho):
+        """log p(Theta, x_ho | G) per particle (g [n, d, d], theta batch) on held-out observational data
+        (svgd.py:475-476 -- the reference's name notwithstanding it calls interventional_log_joint_prob)."""
+        return self._score_held_out(g, theta, x_ho, None)
+
+    def eltwise_log_likelihood_interv(self, g, theta, x_ho, interv_msk_ho):
+        """log p(Theta, x_ho | G) per particle on held-out interventional data (svgd.py:477-478)."""
+        return self._score_held_out(g, theta, x_ho, interv_msk_ho)
 
     def sample(self, *, key, n_particles, steps, n_dim_particles=None, callback=None, callback_every=None):
         """SVGD with DiBS: samples (G, Theta) ~ p(G, Theta | D); returns (int32 [M, d, d], theta pytree) (svgd.py:730-795)."""

@@ -85,6 +85,10 @@ int dibs_abi_version(void);
 int dibs_plan_create(const dibs_config* cfg, dibs_plan** out);
 int dibs_plan_destroy(dibs_plan* plan);
 int dibs_theta_dim(const dibs_plan* plan);
+/* Health of the plan's multi-GPU exchange: DIBS_ERR_STATE once a bounded wait on a peer's rows timed out (a rank
+ * died or ran a different number of steps; DIBS_B200_PEER_TIMEOUT_MS, default 10 s), DIBS_OK otherwise.  The
+ * reference is single-process and has no counterpart; the closest is the exception a failed jax collective raises. */
+int dibs_plan_status(dibs_plan* plan);
 
 /* replaces: the `x=` / `interv_mask=` constructor arguments (svgd.py:86-92, 451-457).
  * x float32 [n_obs, d]; interv_mask int32 [n_obs, d] or NULL (= zeros); bge_mean_obs_host
@@ -104,6 +108,9 @@ int dibs_plan_attach_nccl(dibs_plan* plan, const uint8_t* id128_host);
  * all_handles: world_size x 320 bytes in rank order. */
 int dibs_plan_ipc_export(dibs_plan* plan, uint8_t* handles_out_host);
 int dibs_plan_ipc_attach(dibs_plan* plan, const uint8_t* all_handles_host);
+/* Undo dibs_plan_ipc_attach (also after a partial failure): close every opened peer buffer and return the plan to
+ * the state in which dibs_plan_attach_nccl can be used instead. */
+int dibs_plan_ipc_detach(dibs_plan* plan);
 
 /* ---- the hot loop ---------------------------------------------------------------------------
  * replaces: _svgd_loop -> lax.fori_loop over _svgd_step (svgd.py:226-272, 673-727).
@@ -178,6 +185,12 @@ int dibs_grad_latent_prior(dibs_plan* plan, const float* z, int32_t t, const uin
                            int32_t constraint_only, float* grad_out, void* stream);
 /* acyclic_constr_nograd (graph_utils.py:8-28), vmapped: g float32 [n, d, d] -> h [n] */
 int dibs_acyclic_constr(dibs_plan* plan, const float* g, int32_t n, float* h_out, void* stream);
+/* Progress summary for the callback path, replacing the host-side body of DiBS.visualize_callback (dibs.py:661-692:
+ * particle_to_g_lim + edge_probs + `(elwise_acyclic_constr_nograd(gs) > 0).sum()`): z [n, d, k, 2], t ->
+ * summary_host float32 [2 + d*d] in PINNED host memory = { #particles whose G_lim is cyclic, n, mean edge
+ * probabilities }.  Enqueues two kernels and an asynchronous copy on `stream`; never synchronises (except to grow its
+ * scratch), so a callback does not stall the step loop -- read the record after an event recorded behind this call. */
+int dibs_particle_summary(dibs_plan* plan, const float* z, int32_t n, int32_t t, float* summary_host, void* stream);
 /* _f_kernel_mat (svgd.py:165-176, 537-551; kernel.py:20-30, 52-71):
  * z [n, d*k*2], theta [n, theta_dim] or NULL -> K [n, n] */
 int dibs_kernel_matrix(dibs_plan* plan, const float* z, const float* theta, int32_t n, float* k_out, void* stream);

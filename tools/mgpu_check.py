@@ -12,7 +12,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-OUT = os.path.join(ROOT, "gpurun_out")
+OUT = os.environ.get("MGPU_OUT") or os.path.join(ROOT, "gpurun_out")
 CASES = {"lin": dict(d=20, m=64, s=32, steps=7), "bge": dict(d=12, m=32, s=16, steps=5), "nn": dict(d=10, m=16, s=8, steps=4)}
 
 
@@ -27,10 +27,19 @@ def run():
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # MGPU_SAME_GPU=1: every rank on cuda:0 (time-sliced contexts) with a gloo process group -- NCCL refuses two ranks on
+    # one device, the peer-memory exchange (CUDA IPC between processes) does not care; lets a ONE-GPU box run the
+    # multi-rank path (kernels_peer.cuh) end to end
+    same = os.environ.get("MGPU_SAME_GPU") == "1"
+    if same:
+        local = 0
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if same:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     os.makedirs(OUT, exist_ok=True)
     for name in os.environ.get("MGPU_CASES", "bge,lin,nn").split(","):
         c = CASES[name]
@@ -46,6 +55,10 @@ def run():
             model = MarginalDiBS(x=x, graph_model=gm, likelihood_model=BGe(n_vars=d), n_grad_mc_samples=c["s"])
         model.sample(key=PRNGKey(3), n_particles=c["m"], steps=c["steps"], callback_every=None)
         st = model._last_state
+        if world > 1 and os.environ.get("MGPU_EXPECT"):
+            from dibs_b200.inference.dibs import _PLAN_CACHE
+            kinds = {p.exchange for p in _PLAN_CACHE.values() if p.cfg.world_size > 1}
+            assert kinds == {os.environ["MGPU_EXPECT"]}, kinds
         if int(os.environ.get("RANK", "0")) == 0:
             np.savez(os.path.join(OUT, f"mgpu_w{world}_{name}.npz"), z=st["z"].cpu().numpy(),
                      theta=st["theta"].cpu().numpy() if st["theta"] is not None else np.zeros(0))
