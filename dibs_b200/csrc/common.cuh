@@ -6,6 +6,9 @@
 
 namespace dibs {
 
+// modes of a Monte-Carlo pass (kernels_mc*.cuh) -- also the estimator tag of the assemble step
+enum { MC_THETA_HARD = 0, MC_Z_SCORE = 1, MC_Z_REPARAM = 2, MC_LP_ONLY = 3 };
+
 // ------------------------------------------------------------------------------------------
 // per-step device state: the loop carry of lax.fori_loop that kernels read (svgd.py:226,272)
 // ------------------------------------------------------------------------------------------

@@ -3,6 +3,7 @@
 
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -144,7 +145,6 @@ struct dibs_plan {
     // LinearGaussian, observational data, n_vars > 32: dense Rx and Rx^T on the device (kernels_dense.cuh)
     bool use_dense = false;
     float* rx_dense = nullptr;
-    float* dense_scratch = nullptr;    // DIBS_B200_DENSE_V2 experiment: [M_loc][max_chunks][2][d*d]
     // MC workspace
     int max_chunks = 1, th_acc_size = 0;
     float *th_acc = nullptr, *th_stats = nullptr, *z_acc = nullptr, *z_stats = nullptr, *acyc = nullptr;
@@ -153,6 +153,9 @@ struct dibs_plan {
     float *dist_part = nullptr, *kz = nullptr, *kt = nullptr, *kfull = nullptr;
     int n_jsplit = 1, j_len = 0;
     float* phi_part = nullptr;     // [n_jsplit][M_loc][D]
+    // arrival counters of the in-kernel reductions (zero between launches): gradient CTAs per particle (fused
+    // assemble), feature splits per K tile, j slices per phi tile
+    uint32_t *arrive = nullptr, *dist_cnt = nullptr, *phi_cnt = nullptr;
     // CUDA graphs of one step, per buffer parity
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
     int kernels_per_step = 0;
@@ -198,31 +201,13 @@ static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // CTAs per particle of the acyclicity pass (a function of (A, d, PRNG layout) only)
 constexpr int ACYC_WPC = 4;      // warps (= sample pairs) per CTA of the row-per-lane kernel
 
-// tuning knobs for sweeps without a rebuild (defaults = the values the shapes were measured with):
-//   DIBS_B200_MC_CTAS_PER_SM   target CTAs per SM of a Monte-Carlo pass (scales the number of sample chunks)
-//   DIBS_B200_PHI_CTAS         target CTA count of the phi pass (scales the number of j slices)
-static int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    if (!e || !*e) return dflt;
-    const int v = atoi(e);
-    return v > 0 ? v : dflt;
-}
-static int mc_target_ctas(int dflt_per_sm) {
-    static const int per_sm = env_int("DIBS_B200_MC_CTAS_PER_SM", 0);
-    return (per_sm > 0 ? per_sm : dflt_per_sm) * 148;
-}
+static int mc_target_ctas(int per_sm) { return per_sm * 148; }
 static bool acyc_rows_path(const dibs_plan* p) {
-    return p->d <= 32 && (p->cfg.n_acyclicity_mc_samples % 2) == 0 && !p->cfg.prng_partitionable && !getenv("DIBS_B200_OLD_ACYCLIC");
-}
-// experiment switch (default off): run the 4 x 4 register-tile kernel for n_vars <= 32 as well (one warp per sample)
-static bool acyc_tile_small() {
-    static const bool on = getenv("DIBS_B200_ACYC_TILE") && getenv("DIBS_B200_ACYC_TILE")[0] == '1';
-    return on;
+    return p->d <= 32 && (p->cfg.n_acyclicity_mc_samples % 2) == 0 && !p->cfg.prng_partitionable;
 }
 static int acyc_chunks(const dibs_plan* p) {
-    if ((p->d > 32 && p->d <= 64) || (p->d <= 32 && acyc_tile_small()))
-        return acyc_dense4_shape(p->d, p->cfg.n_acyclicity_mc_samples).chunks;
-    if (p->d > 32) return acyc_dense_shape(p->d, p->cfg.n_acyclicity_mc_samples).chunks;
+    if (p->d > 32 && p->d <= 64) return acyc_dense4_shape(p->d, p->cfg.n_acyclicity_mc_samples).chunks;
+    if (p->d > 64) return acyc_dense_shape(p->d, p->cfg.n_acyclicity_mc_samples).chunks;
     return acyc_rows_path(p) ? ceil_div(p->cfg.n_acyclicity_mc_samples / 2, ACYC_WPC) : 1;
 }
 
@@ -308,17 +293,13 @@ static McShape mc_shape_for(bool qr, int likelihood, int d, int hidden, int n_lo
     return sh;
 }
 
-static bool dense_v2() {
-    static const bool on = getenv("DIBS_B200_DENSE_V2") && getenv("DIBS_B200_DENSE_V2")[0] == '1';   // experiment, default off
-    return on;
-}
-
 static McShape mc_shape_dense(int d, int n_local, int S, bool pair_ok = false) {
     McShape sh;
     sh.qr = false; sh.dense = true;
-    sh.paired = dense_v2() && pair_ok && (S % 2) == 0;
+    sh.paired = false;
+    (void)pair_ok;
     if (n_local < 1) n_local = 1;
-    const int U = sh.paired ? S / 2 : S;                 // units per particle: samples, or sample pairs (experiment)
+    const int U = S;                                     // units per particle: samples
     int want = ceil_div(mc_target_ctas(4), n_local);
     if (want > U) want = U;
     if (want < 1) want = 1;
@@ -371,8 +352,8 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
     p->lognorm_param = logf(6.283185307179586f * p->sig2_param);
     p->er_coef = logf(c.er_p) - logf(1.0f - c.er_p);       // NaN / inf for p >= 1 like graph.py:108
     p->sigma_z2 = powf(c.latent_prior_std, 2.0f);           // latent_prior_std ** 2.0 (dibs.py:657)
-    if (const char* e = getenv("DIBS_B200_NO_GRAPH")) p->use_graph = !(e[0] == '1');
-    if (const char* e = getenv("DIBS_B200_SERIAL")) p->concurrent = !(e[0] == '1');
+    if (const char* e = getenv("DIBS_B200_NO_GRAPH")) p->use_graph = !(e[0] == '1');      // debugging: eager launches
+    if (const char* e = getenv("DIBS_B200_SERIAL")) p->concurrent = !(e[0] == '1');       // debugging: no sibling branches
 
     const int d = p->d, S = c.n_grad_mc_samples;
     {
@@ -414,7 +395,7 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
     {
         const int col_tiles = ceil_div(p->Dz, PT_C) + ceil_div(p->Dth, PT_C);
         const int row_scale = p->M / 256 > 1 ? p->M / 256 : 1;
-        static const int phi_ctas = env_int("DIBS_B200_PHI_CTAS", 592);
+        const int phi_ctas = 592;                       // ~4 CTAs of 128 threads per SM
         int ns = ceil_div(phi_ctas, col_tiles * row_scale);
         const int max_ns = p->M / 64 > 1 ? p->M / 64 : 1;
         if (ns > max_ns) ns = max_ns;
@@ -463,7 +444,10 @@ static int ensure_step_ws(dibs_plan* p) {
         (r = alloc((void**)&p->acyc, (size_t)p->M_loc * acyc_chunks(p) * d * d * sizeof(float))))
         return r;
     size_t plane = (size_t)p->M_loc * p->M * sizeof(float);
-    if ((r = alloc((void**)&p->dist_part, plane * p->n_split)) || (r = alloc((void**)&p->kz, plane)) ||
+    if ((r = alloc((void**)&p->arrive, (size_t)p->M_loc * sizeof(uint32_t))) ||
+        (r = alloc((void**)&p->dist_cnt, (size_t)ceil_div(p->M, KT) * ceil_div(p->M_loc, KT) * sizeof(uint32_t))) ||
+        (r = alloc((void**)&p->phi_cnt, (size_t)(ceil_div(p->Dz, PT_C) + ceil_div(p->Dth, PT_C)) * ceil_div(p->M_loc, PB_I) * sizeof(uint32_t))) ||
+        (r = alloc((void**)&p->dist_part, plane * p->n_split)) || (r = alloc((void**)&p->kz, plane)) ||
         (r = alloc((void**)&p->kt, plane)) || (r = alloc((void**)&p->kfull, plane)) ||
         (r = alloc((void**)&p->phi_part, (size_t)p->n_jsplit * p->M_loc * p->D * sizeof(float))))
         return r;
@@ -506,7 +490,7 @@ extern "C" int dibs_plan_destroy(dibs_plan* p) {
     for (int i = 0; i < 3; ++i) { if (p->aux[i]) cudaStreamDestroy(p->aux[i]); if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]); }
     for (int i = 0; i < 2; ++i) if (p->ev_fork[i]) cudaEventDestroy(p->ev_fork[i]);
     if (p->peer_error) cudaFreeHost(p->peer_error);
-    void* ptrs[] = {p->summary_ws, p->dense_scratch, p->rx_dense, p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->gk[0], p->gk[1], p->peer_flags_local, p->peer_epoch, p->peer_counter, p->v, p->base, p->st, p->step_keys, p->scores,
+    void* ptrs[] = {p->summary_ws, p->arrive, p->dist_cnt, p->phi_cnt, p->rx_dense, p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->gk[0], p->gk[1], p->peer_flags_local, p->peer_epoch, p->peer_counter, p->v, p->base, p->st, p->step_keys, p->scores,
                     p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->dist_part, p->kz, p->kt, p->kfull, p->phi_part};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
@@ -567,7 +551,7 @@ extern "C" int dibs_set_data(dibs_plan* p, const float* x, const int32_t* mask, 
         }
     }
     p->use_qr = false;
-    if (qr_eligible(p->cfg.likelihood, p->dmax) && !p->has_mask && !getenv("DIBS_B200_NO_QR")) {
+    if (qr_eligible(p->cfg.likelihood, p->dmax) && !p->has_mask) {
         std::vector<float> hx((size_t)n_obs * d);
         CU(cudaMemcpyAsync(hx.data(), p->x, hx.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
@@ -575,8 +559,7 @@ extern "C" int dibs_set_data(dibs_plan* p, const float* x, const int32_t* mask, 
         p->use_qr = true;
     }
     p->use_dense = false;
-    if (p->cfg.likelihood == DIBS_LIK_LINEAR_GAUSSIAN && d > 32 && !p->has_mask && lin_dense_smem(d) <= 227 * 1024 &&
-        !getenv("DIBS_B200_NO_QR")) {
+    if (p->cfg.likelihood == DIBS_LIK_LINEAR_GAUSSIAN && d > 32 && !p->has_mask && lin_dense_smem(d) <= 227 * 1024) {
         std::vector<float> hx((size_t)n_obs * d), packed;
         CU(cudaMemcpyAsync(hx.data(), p->x, hx.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
@@ -594,10 +577,6 @@ extern "C" int dibs_set_data(dibs_plan* p, const float* x, const int32_t* mask, 
         CU(cudaMemcpyAsync(p->rx_dense, dense.data(), dense.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
         CU(cudaStreamSynchronize(stream));
         p->use_dense = true;
-        if (dense_v2()) {
-            if (p->dense_scratch) { cudaFree(p->dense_scratch); p->dense_scratch = nullptr; }
-            CU(cudaMalloc((void**)&p->dense_scratch, (size_t)p->M_loc * p->max_chunks * 2 * d * d * sizeof(float)));
-        }
     }
     if (p->cfg.likelihood == DIBS_LIK_BGE) TRY(bge_prepare(p->cfg, d, n_obs, p->x, p->mask, bge_mean_obs_host, &p->bge_r,
                                                        &p->bge_table, &p->bge_coef, &p->bge_r_stride, stream, g_last_error));
@@ -678,11 +657,11 @@ static int launch_mc(const dibs_plan* p, McParams q, const McShape& sh, cudaStre
     const int lik = p->cfg.likelihood;
     size_t smem = 0;
     int e = 0;
+    // a fused launch (step loop) also needs room for the assemble step its last CTA per particle runs
+    const size_t fuse_smem = q.fuse.arrive ? assemble_smem(p->d, p->k, q.fuse.a.z_chunks, q.fuse.a.th_chunks) : 0;
     if (sh.dense) {
-        q.dense_v2 = (dense_v2() && p->dense_scratch && q.n_local <= p->M_loc && q.n_chunks <= p->max_chunks) ? 1 : 0;
-        q.dense_scratch = p->dense_scratch;
-        if (!q.dense_v2) q.paired = 0;
-        smem = lin_dense_smem(p->d);
+        q.paired = 0;
+        smem = std::max(lin_dense_smem(p->d), fuse_smem);
         auto kern = k_mc_lin_dense<MODE>;
         TRY(set_smem(kern, smem));
         kern<<<grid, sh.threads, smem, stream>>>(q, p->rx_dense, dense_ld(p->d), dense_nt(p->d));
@@ -690,7 +669,7 @@ static int launch_mc(const dibs_plan* p, McParams q, const McShape& sh, cudaStre
         return DIBS_OK;
     }
     if (sh.qr) {
-        smem = mc_lin_qr_smem(p->dmax, q.gpb);
+        smem = std::max(mc_lin_qr_smem(p->dmax, q.gpb), fuse_smem);
         if (smem > 227 * 1024) return fail(DIBS_ERR_UNSUPPORTED, "problem size needs more than 227 KB of shared memory per CTA");
         switch (p->dmax) {
             case 8: e = launch_mc_linqr_8(MODE, q, grid, sh.threads, smem, p->lin_r.data(), stream); break;
@@ -710,6 +689,7 @@ static int launch_mc(const dibs_plan* p, McParams q, const McShape& sh, cudaStre
         if (MODE != MC_Z_SCORE && MODE != MC_LP_ONLY) return fail(DIBS_ERR_UNSUPPORTED, "BGe supports the score estimator only");
         smem = mc_bge_smem(p->d, p->dmax, q.s_per_chunk * (q.paired ? 2 : 1), p->bge_r_stride == 0);
     }
+    smem = std::max(smem, fuse_smem);
     if (smem > 227 * 1024) return fail(DIBS_ERR_UNSUPPORTED, "problem size needs more than 227 KB of shared memory per CTA");
 #define GO(FAM) switch (p->dmax) { case 8: e = launch_mc_##FAM##_8(MODE, q, grid, smem, stream); break; \
         case 16: e = launch_mc_##FAM##_16(MODE, q, grid, smem, stream); break; \
@@ -729,7 +709,8 @@ static int launch_mc(const dibs_plan* p, McParams q, const McShape& sh, cudaStre
     return DIBS_OK;
 }
 
-static int launch_acyc(const dibs_plan* p, const Src& s, int which_split, float* ds_out, cudaStream_t stream) {
+static int launch_acyc(const dibs_plan* p, const Src& s, int which_split, float* ds_out, cudaStream_t stream,
+                       const FuseAsm* fuse = nullptr) {
     AcycParams a;
     memset(&a, 0, sizeof(a));
     a.z = s.z; a.z_ld = s.z_ld; a.scores = s.scores; a.n_local = s.n; a.m_offset = s.m_offset; a.n_particles = p->M;
@@ -737,45 +718,41 @@ static int launch_acyc(const dibs_plan* p, const Src& s, int which_split, float*
     a.st = s.st; a.which_split = which_split; a.partitionable = p->cfg.prng_partitionable;
     a.keys_override = pass_keys(s, which_split); a.t_override = s.t;
     a.alpha_linear = p->cfg.alpha_linear; a.tau = p->cfg.tau; a.ds_out = ds_out;
+    if (fuse) a.fuse = *fuse;
+    const size_t fuse_smem = fuse ? assemble_smem(p->d, p->k, fuse->a.z_chunks, fuse->a.th_chunks) : 0;
     const int d = p->d;
-    if (d <= 32 && acyc_tile_small()) {
-        const AcycDenseShape sh = acyc_dense4_shape(d, a.n_samples);
-        TRY(set_smem(k_acyclic_dense4, sh.smem));
-        const int paired = (!a.partitionable && (a.n_samples % 2) == 0 && (sh.rounds % 2) == 0 &&
-                            sh.chunks * sh.rounds == a.n_samples) ? 1 : 0;
-        k_acyclic_dense4<<<dim3(s.n, sh.chunks), sh.threads, sh.smem, stream>>>(a, sh.ld, sh.nt, sh.rounds, paired);
-    } else if (acyc_rows_path(p)) {
+    if (acyc_rows_path(p)) {
         // row-per-lane kernel: a warp per sample pair (both lanes of each threefry block are used)
         const int warps = ACYC_WPC;
-        size_t smem = acyclic_rows_smem(d, p->k, p->dmax, warps);
+        const size_t smem = std::max(acyclic_rows_smem(d, p->k, p->dmax, warps), fuse_smem);
         dim3 grid(s.n, acyc_chunks(p));
-        static const int minb = getenv("DIBS_B200_ACYC_MINB") ? atoi(getenv("DIBS_B200_ACYC_MINB")) : 4;
-#define ACYC_GO(DM, MB) { TRY(set_smem(k_acyclic_rows<DM, MB>, smem)); k_acyclic_rows<DM, MB><<<grid, warps * 32, smem, stream>>>(a); }
-#define ACYC_DM(DM) { if (minb >= 6) ACYC_GO(DM, 6) else if (minb == 5) ACYC_GO(DM, 5) else ACYC_GO(DM, 4) }
+#define ACYC_GO(DM) { TRY(set_smem(k_acyclic_rows<DM>, smem)); k_acyclic_rows<DM><<<grid, warps * 32, smem, stream>>>(a); }
         switch (p->dmax) {
-            case 8: ACYC_DM(8) break;
-            case 16: ACYC_DM(16) break;
-            case 20: ACYC_DM(20) break;
-            default: ACYC_DM(32) break;
+            case 8: ACYC_GO(8) break;
+            case 16: ACYC_GO(16) break;
+            case 20: ACYC_GO(20) break;
+            default: ACYC_GO(32) break;
         }
-#undef ACYC_DM
 #undef ACYC_GO
     } else if (d <= 32) {
         int warps = a.n_samples < 8 ? a.n_samples : 8;
         size_t smem = acyclic_smem(d, p->k, warps);
         while (smem > 200 * 1024 && warps > 1) { warps /= 2; smem = acyclic_smem(d, p->k, warps); }
+        smem = std::max(smem, fuse_smem);
         TRY(set_smem(k_acyclic_grad<true>, smem));
         k_acyclic_grad<true><<<s.n, warps * 32, smem, stream>>>(a);
     } else if (d <= 64) {
         // 4 x 4 register tiles: one sample per CTA at a time, several CTAs per SM
         const AcycDenseShape sh = acyc_dense4_shape(d, a.n_samples);
-        TRY(set_smem(k_acyclic_dense4, sh.smem));
-        k_acyclic_dense4<<<dim3(s.n, sh.chunks), sh.threads, sh.smem, stream>>>(a, sh.ld, sh.nt, sh.rounds, 0);
+        const size_t smem = std::max(sh.smem, fuse_smem);
+        TRY(set_smem(k_acyclic_dense4, smem));
+        k_acyclic_dense4<<<dim3(s.n, sh.chunks), sh.threads, smem, stream>>>(a, sh.ld, sh.nt, sh.rounds);
     } else {
         // register-tiled matrix powers on shared-memory operands (kernels_dense.cuh)
         const AcycDenseShape sh = acyc_dense_shape(d, a.n_samples);
-        TRY(set_smem(k_acyclic_dense, sh.smem));
-        k_acyclic_dense<<<dim3(s.n, sh.chunks), sh.threads, sh.smem, stream>>>(a, sh.ld, sh.nt, sh.ng, sh.rounds);
+        const size_t smem = std::max(sh.smem, fuse_smem);
+        TRY(set_smem(k_acyclic_dense, smem));
+        k_acyclic_dense<<<dim3(s.n, sh.chunks), sh.threads, smem, stream>>>(a, sh.ld, sh.nt, sh.ng, sh.rounds);
     }
     LAUNCHED();
     return DIBS_OK;
@@ -832,13 +809,30 @@ static int ensure_aux(dibs_plan* p) {
     return DIBS_OK;
 }
 
-// gradient phase for `s.n` particles: MC passes | acyclicity (independent: sibling streams when `conc`) -> assemble
+// gradient phase for `s.n` particles: MC passes | acyclicity (independent: sibling streams when `conc`); the assemble
+// step of a particle runs inside whichever of its gradient CTAs finishes last (fuse_arrive, kernels_prior.cuh)
 static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_stats, float* z_acc, float* z_stats,
                          float* acyc, const float* base_in, float* base_out, float* grad_z, int gz_ld, float* grad_th,
                          int gth_ld, cudaStream_t stream, bool conc, uint32_t* next_keys, StepState* st_next,
                          const PeerPush* push = nullptr) {
     const bool joint = p->cfg.joint;
     const McShape sh = mc_shape(p, s.n, p->cfg.n_grad_mc_samples, false);
+    FuseAsm fuse;
+    memset(&fuse, 0, sizeof(fuse));
+    AsmParams& a = fuse.a;
+    fill_asm(p, s, a);
+    a.zacc = z_acc; a.zstats = z_stats; a.z_chunks = sh.chunks;
+    a.baselines_in = base_in; a.baselines_out = base_out;
+    if (joint) { a.thacc = th_acc; a.thstats = th_stats; a.th_chunks = sh.chunks; a.th_dim = p->Dth; }
+    a.acyc = acyc; a.acyc_chunks = acyc_chunks(p);
+    a.grad_z = grad_z; a.gz_ld = gz_ld; a.grad_th = grad_th; a.gth_ld = gth_ld;
+    a.next_keys = next_keys; a.st_next = st_next;
+    a.n_step_splits = joint ? 3 : 2; a.n_particles = p->M; a.partitionable = p->cfg.prng_partitionable;
+    a.m_offset = s.m_offset; a.pre_split_mask = joint ? 2u : 1u;
+    if (push) a.push = *push;
+    fuse.arrive = p->arrive;
+    fuse.total = (joint ? sh.chunks : 0) + sh.chunks + a.acyc_chunks;
+
     McParams q;
     cudaStream_t s_th = conc ? p->aux[0] : stream, s_ac = conc ? p->aux[1] : stream;
     if (conc) {
@@ -850,34 +844,23 @@ static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_st
         fill_mc(p, s, q);
         q.which_split = 0; q.keys_override = pass_keys(s, 0);
         q.part_acc = th_acc; q.acc_size = p->th_acc_size; q.part_stats = th_stats;
+        q.fuse = fuse;
         TRY(launch_mc<MC_THETA_HARD>(p, q, sh, s_th));
         mark(p, stream, DIBS_PHASE_MC_THETA);
     }
     fill_mc(p, s, q);
     q.which_split = joint ? 1 : 0; q.keys_override = pass_keys(s, q.which_split);
     q.part_acc = z_acc; q.acc_size = p->d * p->d; q.part_stats = z_stats;
+    q.fuse = fuse;
     if (p->cfg.grad_estimator_z == DIBS_ESTIMATOR_SCORE) TRY(launch_mc<MC_Z_SCORE>(p, q, sh, stream));
     else TRY(launch_mc<MC_Z_REPARAM>(p, q, sh, stream));
     mark(p, stream, DIBS_PHASE_MC_Z);
-    TRY(launch_acyc(p, s, joint ? 2 : 1, acyc, s_ac));
+    TRY(launch_acyc(p, s, joint ? 2 : 1, acyc, s_ac, &fuse));
     mark(p, stream, DIBS_PHASE_ACYCLIC);
     if (conc) {
         if (joint) TRY(stream_edge(s_th, stream, p->ev_join[0]));
         TRY(stream_edge(s_ac, stream, p->ev_join[1]));
     }
-    AsmParams a;
-    fill_asm(p, s, a);
-    a.zacc = z_acc; a.zstats = z_stats; a.z_chunks = sh.chunks;
-    a.baselines_in = base_in; a.baselines_out = base_out;
-    if (joint) { a.thacc = th_acc; a.thstats = th_stats; a.th_chunks = sh.chunks; a.th_dim = p->Dth; }
-    a.acyc = acyc; a.acyc_chunks = acyc_chunks(p);
-    a.grad_z = grad_z; a.gz_ld = gz_ld; a.grad_th = grad_th; a.gth_ld = gth_ld;
-    a.next_keys = next_keys; a.st_next = st_next;
-    a.n_step_splits = joint ? 3 : 2; a.n_particles = p->M; a.partitionable = p->cfg.prng_partitionable;
-    a.m_offset = s.m_offset; a.pre_split_mask = joint ? 2u : 1u;
-    if (push) a.push = *push;
-    TRY(launch_asm(p, a, stream));
-    mark(p, stream, DIBS_PHASE_ASSEMBLE);
     return DIBS_OK;
 }
 
@@ -885,55 +868,29 @@ static void fill_pair(const dibs_plan* p, PairParams& q) {
     memset(&q, 0, sizeof(q));
     q.n_all = p->M; q.row0 = p->row0; q.n_rows = p->M_loc; q.dz = p->Dz; q.dth = p->Dth;
     q.n_split = p->n_split; q.n_split_z = p->n_split_z; q.split_len_z = p->split_len_z; q.split_len_t = p->split_len_t;
-    q.dist_part = p->dist_part;
+    q.dist_part = p->dist_part; q.dist_cnt = p->dist_cnt;
     q.kz = p->kz; q.kt = p->Dth ? p->kt : nullptr; q.kfull = p->kfull;
     q.h_z = p->cfg.h_latent; q.h_t = p->cfg.h_theta; q.scale_z = p->cfg.scale_latent; q.scale_t = p->cfg.scale_theta;
-    q.n_jsplit = p->n_jsplit; q.j_len = p->j_len; q.phi_part = p->phi_part;
+    q.n_jsplit = p->n_jsplit; q.j_len = p->j_len; q.phi_part = p->phi_part; q.phi_cnt = p->phi_cnt;
+    q.optimizer = p->cfg.optimizer; q.stepsize = p->cfg.stepsize;
 }
 
-static void fill_update(const dibs_plan* p, const PairParams& q, UpdateParams& u) {
-    memset(&u, 0, sizeof(u));
-    u.phi_part = q.phi_part; u.n_jsplit = q.n_jsplit; u.n_rows = q.n_rows; u.dz = q.dz; u.dth = q.dth; u.n_all = q.n_all;
-    u.x_cur = q.x_all + (size_t)q.row0 * q.ld; u.ld = q.ld;
-    u.optimizer = p->cfg.optimizer; u.stepsize = p->cfg.stepsize;
-    u.d = p->d; u.k = p->k;
-}
-
+// kernel matrix of the rank's rows against all particles: squared distances per feature split, finished into
+// K_z, K_theta, K by each tile's last split CTA
 static int launch_kmat(dibs_plan* p, const PairParams& q, cudaStream_t stream) {
     dim3 g1(ceil_div(q.n_all, KT), ceil_div(q.n_rows, KT), q.n_split);
     k_pair_dist<<<g1, 256, 0, stream>>>(q);
     LAUNCHED();
     mark(p, stream, DIBS_PHASE_PAIR_DIST);
-    size_t plane = (size_t)q.n_rows * q.n_all;
-    int blocks = (int)((plane + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-    k_pair_finish<<<blocks, 256, 0, stream>>>(q);
-    LAUNCHED();
-    mark(p, stream, DIBS_PHASE_PAIR_KERNEL);
     return DIBS_OK;
 }
 
+// phi partial sums per j slice, finished (mean, optimizer step, peer push) by each tile's last slice CTA
 static int launch_phi(dibs_plan* p, const PairParams& q, cudaStream_t stream) {
-    static const bool big = getenv("DIBS_B200_PHI_TILE") && getenv("DIBS_B200_PHI_TILE")[0] == '1';   // experiment, default off
-    if (big) {
-        dim3 gb(ceil_div(q.dz, PT_C) + ceil_div(q.dth, PT_C), ceil_div(q.n_rows, PB_I), q.n_jsplit);
-        k_phi_partial_big<<<gb, 128, 0, stream>>>(q);
-        LAUNCHED();
-        mark(p, stream, DIBS_PHASE_PHI_UPDATE);
-        return DIBS_OK;
-    }
-    dim3 g3(ceil_div(q.dz, PT_C) + ceil_div(q.dth, PT_C), ceil_div(q.n_rows, PT_I), q.n_jsplit);
-    k_phi_partial<<<g3, 128, 0, stream>>>(q);
+    dim3 gb(ceil_div(q.dz, PT_C) + ceil_div(q.dth, PT_C), ceil_div(q.n_rows, PB_I), q.n_jsplit);
+    k_phi<<<gb, 128, 0, stream>>>(q);
     LAUNCHED();
     mark(p, stream, DIBS_PHASE_PHI_UPDATE);
-    return DIBS_OK;
-}
-
-static int launch_update(dibs_plan* p, const UpdateParams& u, cudaStream_t stream) {
-    size_t smem = u.scores ? (size_t)2 * u.d * u.k * sizeof(float) : 0;
-    TRY(set_smem(k_opt_update, smem));
-    k_opt_update<<<u.n_rows, 256, smem, stream>>>(u);
-    LAUNCHED();
-    mark(p, stream, DIBS_PHASE_STEP_KEYS);
     return DIBS_OK;
 }
 
@@ -984,24 +941,19 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream, bool conc) {
     fill_pair(p, q);
     q.x_all = P; q.ld = p->ld; q.g_all = G; q.g_ld = p->ld;
     q.wait_x = make_wait(p, PEER_KIND_X); q.wait_g = make_wait(p, PEER_KIND_GRAD);
-    // the kernel matrix needs the particles only: it runs on a side branch under the gradient phase; on several GPUs
-    // the particle rows every rank updated at the end of the previous step arrive by peer pushes (the kernel waits
-    // on their flags) or, on the NCCL path, by an all-gather at the head of the branch
+    // the kernel matrix needs the particles only: it runs on a side branch under the gradient phase.  On several GPUs
+    // the rows every rank updated at the end of the previous step were stored into this rank's buffer by the peers'
+    // phi kernels (the distance kernel waits on their flags) or, on the NCCL path, arrive by an all-gather here
     cudaStream_t s_k = conc ? p->aux[2] : stream;
     if (conc) TRY(stream_edge(stream, s_k, p->ev_fork[0]));
-    if (multi) {
-        // the branch starts by publishing the rows this rank updated at the end of the previous step (or packed at
-        // the start of the call): off the critical path, under the gradient phase
-        if (p->p2p) TRY(launch_push(p, PEER_KIND_X, P, p->peer_pk[cur], s_k));
-        else NC(g_nccl.AllGather(loc, P, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm_x, s_k));
+    if (multi && !p->p2p) {
+        NC(g_nccl.AllGather(loc, P, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm_x, s_k));
         mark(p, s_k, DIBS_PHASE_ALLGATHER);
     }
     TRY(launch_kmat(p, q, s_k));
     Src s{loc, p->ld, p->Dth ? loc + p->Dz : nullptr, p->ld, p->M_loc, p->row0, st, nullptr, 0, p->step_keys, p->scores};
-    // peer-memory path: the producing kernels store their rows into every peer themselves (fused exchange) unless
-    // DIBS_B200_PUSH_KERNEL=1 asks for the separate copy kernel
-    static const bool fused_push = !(getenv("DIBS_B200_PUSH_KERNEL") && getenv("DIBS_B200_PUSH_KERNEL")[0] == '1');
-    const bool fuse = multi && p->p2p && fused_push;
+    // peer-memory path: the producing kernels store their rows into every peer themselves (fused exchange)
+    const bool fuse = multi && p->p2p;
     PeerPush push_g;
     if (fuse) fill_push(p, push_g, PEER_KIND_GRAD, p->peer_gk[cur]);
     TRY(enqueue_grads(p, s, p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->base, p->base,
@@ -1009,19 +961,17 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream, bool conc) {
                       p->st + (cur ^ 1), fuse ? &push_g : nullptr));
     if (multi && !fuse) {
         // the one exchange on the critical path: every rank contributes its gradient rows [dZ | dTheta]
-        if (p->p2p) TRY(launch_push(p, PEER_KIND_GRAD, G, p->peer_gk[cur], stream));
-        else NC(g_nccl.AllGather(gloc, G, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm, stream));
+        NC(g_nccl.AllGather(gloc, G, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm, stream));
         mark(p, stream, DIBS_PHASE_ALLGATHER);
     }
     if (conc) TRY(stream_edge(s_k, stream, p->ev_join[2]));
+    q.x_next = Pn + (size_t)p->row0 * p->ld; q.next_ld = p->ld;
+    q.v = p->v; q.v_ld = p->D;
+    if (fuse) fill_push(p, q.push_x, PEER_KIND_X, p->peer_pk[cur ^ 1]);
     TRY(launch_phi(p, q, stream));
-    UpdateParams u;
-    fill_update(p, q, u);
-    u.x_next = Pn + (size_t)p->row0 * p->ld; u.next_ld = p->ld;
-    u.v = p->v; u.v_ld = p->D;
-    u.scores = p->scores;
-    u.row0 = p->row0;
-    TRY(launch_update(p, u, stream));
+    // raw scores U V^T of the NEXT step from the updated latent rows (edge-probability pass, dibs.py:179-181)
+    TRY(launch_prologue(p, q.x_next, p->ld, p->M_loc, p->row0, nullptr, nullptr, 0, 0u, p->scores, nullptr, stream));
+    mark(p, stream, DIBS_PHASE_STEP_KEYS);
     return DIBS_OK;
 }
 
@@ -1069,8 +1019,9 @@ static int svgd_steps_impl(dibs_plan* p, int32_t t_start, int32_t n_steps, float
     TRY(launch_prologue(p, loc0, p->ld, p->M_loc, p->row0, p->st, nullptr, p->cfg.joint ? 3 : 2, p->cfg.joint ? 2u : 1u,
                         p->scores, p->step_keys, stream));
 
-    static const bool nccl_graph = !(getenv("DIBS_B200_NCCL_GRAPH") && getenv("DIBS_B200_NCCL_GRAPH")[0] == '0');
-    const bool graph = p->use_graph && (p->cfg.world_size == 1 || nccl_graph) && !(timed && per_kernel);
+    // peer-memory path: publish the rows this call just packed (later steps: the phi kernel pushes its updated rows)
+    if (p->p2p) TRY(launch_push(p, PEER_KIND_X, p->pk[0], p->peer_pk[0], stream));
+    const bool graph = p->use_graph && !(timed && per_kernel);
     p->ev_used = 0;
     if (graph && !p->gexec[0]) {
         if (p->cfg.world_size > 1 && !p->p2p) {
@@ -1464,6 +1415,7 @@ static int hook_pair(dibs_plan* p, const float* z, const float* theta, const flo
     Scratch sc;
     const int D = p->D;
     float *xs, *gs, *dist, *kz, *kt, *kf, *phi = nullptr;
+    uint32_t* cnt = nullptr;
     TRY(sc.get(&xs, (size_t)n * D));
     TRY(sc.get(&gs, (size_t)n * D));
     const size_t fz = sizeof(float) * p->Dz, ft = sizeof(float) * p->Dth, fd = sizeof(float) * D;
@@ -1476,6 +1428,10 @@ static int hook_pair(dibs_plan* p, const float* z, const float* theta, const flo
     fill_pair(p, q);
     q.n_all = n; q.row0 = 0; q.n_rows = n;
     size_t plane = (size_t)n * n;
+    const size_t n_cnt = (size_t)ceil_div(n, KT) * ceil_div(n, KT) + (size_t)(ceil_div(p->Dz, PT_C) + ceil_div(p->Dth, PT_C)) * ceil_div(n, PB_I);
+    TRY(sc.get(&cnt, n_cnt));
+    CU(cudaMemsetAsync(cnt, 0, n_cnt * sizeof(uint32_t), stream));
+    q.dist_cnt = cnt; q.phi_cnt = cnt + (size_t)ceil_div(n, KT) * ceil_div(n, KT);
     TRY(sc.get(&dist, plane * p->n_split));
     TRY(sc.get(&kz, plane)); TRY(sc.get(&kt, plane));
     if (!k_out) TRY(sc.get(&kf, plane)); else kf = k_out;
@@ -1488,13 +1444,8 @@ static int hook_pair(dibs_plan* p, const float* z, const float* theta, const flo
         q.j_len = ceil_div(n, PT_J) * PT_J; q.n_jsplit = 1;
         TRY(sc.get(&part, (size_t)n * D));
         q.phi_part = part;
+        q.phi_out = phi; q.phi_ld = D;            // phi only: no optimizer step (x_next == null)
         TRY(launch_phi(p, q, stream));
-        UpdateParams u;
-        fill_update(p, q, u);
-        u.phi_out = phi; u.phi_ld = D;
-        TRY(launch_update(p, u, stream));
-    }
-    if (phi_z) {
         CU(cudaMemcpy2DAsync(phi_z, fz, phi, fd, fz, n, cudaMemcpyDeviceToDevice, stream));
         if (phi_th && p->Dth) CU(cudaMemcpy2DAsync(phi_th, ft, phi + p->Dz, fd, ft, n, cudaMemcpyDeviceToDevice, stream));
     }

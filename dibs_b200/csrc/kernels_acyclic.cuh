@@ -42,9 +42,9 @@ __device__ __forceinline__ void row_times_smem(const float (&x)[DMAX], const flo
     for (int j = 0; j < DMAX / 2; ++j) { out[2 * j] = lo2(o2[j]); out[2 * j + 1] = hi2(o2[j]); }
 }
 
-// MINB: CTAs per SM the register allocation is tuned for (128 threads per CTA): 4 -> 128 registers, 5 -> 96, 6 -> 80
-template <int DMAX, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_acyclic_rows(AcycParams p) {
+// 4 CTAs of 128 threads per SM -> 128 registers per thread (96 / 80 registers measured slower: spills in the products)
+template <int DMAX>
+__global__ void __launch_bounds__(128, 4) k_acyclic_rows(const __grid_constant__ AcycParams p) {
     extern __shared__ __align__(16) float smem[];
     static_assert(DMAX % 4 == 0 && DMAX <= 32, "one lane per row, 128-bit row loads");
     const int d = p.d, k = p.k, dd = d * d;
@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(128, MINB) k_acyclic_rows(AcycParams p) {
         for (int w = 0; w < n_warps; ++w) sum += sRed[(size_t)w * dd + e];
         outp[e] = sum;
     }
+    fuse_arrive(p.fuse, m, smem);
 }
 
 inline size_t acyclic_rows_smem(int d, int k, int dmax, int n_warps) {

@@ -109,7 +109,7 @@ static inline AcycDenseShape acyc_dense_shape(int d, int n_samples) {
     return s;
 }
 
-__global__ void __launch_bounds__(256, 1) k_acyclic_dense(AcycParams p, int LD, int NT, int NG, int rounds) {
+__global__ void __launch_bounds__(256, 1) k_acyclic_dense(const __grid_constant__ AcycParams p, int LD, int NT, int NG, int rounds) {
     extern __shared__ __align__(16) float smem[];
     const int d = p.d, dd = d * d, HALF = LD / 2, TQ = HALF / 4;
     const int m = blockIdx.x, tid = threadIdx.x;
@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(256, 1) k_acyclic_dense(AcycParams p, int LD, 
         for (int g = 0; g < NG; ++g) sum += sRed[(size_t)g * MAT + i * LD + j];
         outp[e] = sum;
     }
+    fuse_arrive(p.fuse, m, smem);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -262,11 +263,11 @@ static inline AcycDenseShape acyc_dense4_shape(int d, int n_samples) {
     s.threads = ((s.nt + 31) / 32) * 32;
     s.rounds = (n_samples + 7) / 8;                      // <= 8 chunks per particle, fixed decomposition
     s.chunks = (n_samples + s.rounds - 1) / s.rounds;
-    s.smem = 4 * mat + (size_t)(d <= 32 ? 2 : 1) * d * d * sizeof(float) + 64;   // sS (+ the paired second graph, n_vars <= 32 only)
+    s.smem = 4 * mat + (size_t)d * d * sizeof(float) + 64;
     return s;
 }
 
-__global__ void __launch_bounds__(256, 2) k_acyclic_dense4(AcycParams p, int LD, int NT, int rounds, int paired) {
+__global__ void __launch_bounds__(256, 2) k_acyclic_dense4(const __grid_constant__ AcycParams p, int LD, int NT, int rounds) {
     extern __shared__ __align__(16) float smem[];
     const int d = p.d, dd = d * d, TQ = LD / 4;
     const int m = blockIdx.x, tid = threadIdx.x;
@@ -298,36 +299,12 @@ __global__ void __launch_bounds__(256, 2) k_acyclic_dense4(AcycParams p, int LD,
 #pragma unroll
     for (int a = 0; a < 4; ++a) { acc.c[a][0] = 0ull; acc.c[a][1] = 0ull; }
 
-    // `paired` (legacy threefry layout, A and rounds even): the CTA owns the sample PAIRS (q, q + A/2), q in
-    // [blockIdx.y * rounds/2, ...): both lanes of every threefry block are used, the second graph waits in sG2
-    float* sG2 = sRt + MAT;                              // [dd] raw entries of the pair's second graph (paired only)
-    const uint32_t half = n_total >> 1;
     for (int r = 0; r < rounds; ++r) {
-        int a;
-        if (paired) {
-            const int q = blockIdx.y * (rounds >> 1) + (r >> 1);
-            if (q >= (p.n_samples >> 1)) break;          // CTA-uniform
-            a = q + (r & 1) * (p.n_samples >> 1);
-        } else {
-            a = blockIdx.y * rounds + r;
-            if (a >= p.n_samples) break;                 // CTA-uniform
-        }
+        const int a = blockIdx.y * rounds + r;
+        if (a >= p.n_samples) break;                     // CTA-uniform
         for (int i = tid / d, j = tid - (tid / d) * d, e = tid; e < dd; e += blockDim.x) {
             float g = 0.0f;
-            if (paired) {
-                if ((r & 1) == 0) {
-                    float g1 = 0.0f;
-                    if (i != j) {
-                        const uint32_t e0 = (uint32_t)a * dd + e;
-                        const uint2 bits = threefry2x32(key.x, key.y, e0, e0 + half);
-                        g = entry_from_bits<false>(bits.x, sS[e], fast_soft, p.tau);
-                        g1 = entry_from_bits<false>(bits.y, sS[e], fast_soft, p.tau);
-                    }
-                    sG2[e] = g1;
-                } else {
-                    g = sG2[e];
-                }
-            } else if (i != j) {
+            if (i != j) {
                 const uint32_t bits = jax_bits(key, (uint32_t)a * dd + e, n_total, p.partitionable);
                 g = entry_from_bits<false>(bits, sS[e], fast_soft, p.tau);
             }
@@ -394,6 +371,7 @@ __global__ void __launch_bounds__(256, 2) k_acyclic_dense4(AcycParams p, int LD,
                 if (row < d && col < d) outp[row * d + col] = tile4_get(acc, a4, b);
             }
     }
+    fuse_arrive(p.fuse, m, smem);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -408,7 +386,7 @@ static inline size_t lin_dense_smem(int d) {
 
 // rx: [2][LD][LD] dense Rx (upper triangular) and its transpose, zero padded
 template <int MODE>
-__global__ void __launch_bounds__(256, 1) k_mc_lin_dense(McParams p, const float* __restrict__ rx, int LD, int NT) {
+__global__ void __launch_bounds__(256, 1) k_mc_lin_dense(const __grid_constant__ McParams p, const float* __restrict__ rx, int LD, int NT) {
     extern __shared__ __align__(16) float smem[];
     constexpr bool HARD = (MODE == MC_THETA_HARD || MODE == MC_Z_SCORE);
     const int d = p.d, dd = d * d, HALF = LD / 2, TQ = HALF / 4, MAT = LD * LD;
@@ -445,53 +423,11 @@ __global__ void __launch_bounds__(256, 1) k_mc_lin_dense(McParams p, const float
 
     Tile8 acc; tile_zero(acc);
     float m_run = -INFINITY, l_run = 0.0f, sum_lp = 0.0f;
-    // experiment (DIBS_B200_DENSE_V2=1): sigmoid / exp of the scores once per CTA (per-CTA global scratch, each entry
-    // written and re-read by the same thread), no integer divisions in the draw loop, and -- legacy threefry layout,
-    // even S -- sample PAIRS (q, q + S/2) per CTA so that both lanes of every threefry block are used
-    const bool v2 = p.dense_v2 != 0;
-    const bool paired = v2 && p.paired != 0 && !use_ext;
-    float* sc = v2 ? p.dense_scratch + ((size_t)m * p.n_chunks + c) * 2 * dd : nullptr;
-    if (v2 && !use_ext) {
-        for (int e = tid; e < dd; e += blockDim.x) {
-            const float a = srow ? alpha * srow[e] : 0.0f;
-            sc[e] = HARD ? sigmoidf_ref(a) : (fast_soft ? expf(-a) : a);
-        }
-    }
-    const int n_units = paired ? (S >> 1) : S;
-    const int u_begin = c * p.s_per_chunk, u_end = min(n_units, u_begin + p.s_per_chunk);
-    const int n_it = (u_end - u_begin) * (paired ? 2 : 1);
-    const uint32_t half = n_total >> 1;
+    const int s_begin = c * p.s_per_chunk, s_end = min(S, s_begin + p.s_per_chunk);
     __syncthreads();
 
-    for (int it = 0; it < n_it; ++it) {
-        const int s = paired ? (u_begin + (it >> 1) + (it & 1) * (S >> 1)) : (u_begin + it);
+    for (int s = s_begin; s < s_end; ++s) {
         // ---- draw the graph; U = I - G o Theta
-        if (v2) {
-            for (int i = tid / d, j = tid - (tid / d) * d, e = tid; e < dd; e += blockDim.x) {
-                float g = 0.0f;
-                if (i != j) {
-                    if (use_ext) g = p.g_ext[((size_t)m * S + s) * dd + e];
-                    else if (paired) {
-                        if ((it & 1) == 0) {
-                            const uint32_t e0 = (uint32_t)s * dd + e;
-                            const uint2 bits = threefry2x32(key.x, key.y, e0, e0 + half);
-                            const float sa = sc[e];
-                            g = entry_from_bits<HARD>(bits.x, sa, fast_soft, p.tau);
-                            sc[dd + e] = entry_from_bits<HARD>(bits.y, sa, fast_soft, p.tau);
-                        } else {
-                            g = sc[dd + e];
-                        }
-                    } else {
-                        const uint32_t bits = jax_bits(key, (uint32_t)s * dd + e, n_total, p.partitionable);
-                        g = entry_from_bits<HARD>(bits, sc[e], fast_soft, p.tau);
-                    }
-                }
-                sGm[i * LD + j] = g;
-                sW[i * LD + j] = (i == j ? 1.0f : 0.0f) - g * sTh[i * LD + j];
-                j += blockDim.x;
-                while (j >= d) { j -= d; ++i; }
-            }
-        } else {
         for (int e = tid; e < dd; e += blockDim.x) {
             const int i = e / d, j = e - i * d;
             float g = 0.0f;
@@ -506,7 +442,6 @@ __global__ void __launch_bounds__(256, 1) k_mc_lin_dense(McParams p, const float
             }
             sGm[i * LD + j] = g;
             sW[i * LD + j] = (i == j ? 1.0f : 0.0f) - g * sTh[i * LD + j];
-        }
         }
         __syncthreads();
         // ---- prior column partials of the tile rows: sum_i g logN(theta; mean_edge, sig_edge)  (linearGaussian.py:289)
@@ -627,6 +562,7 @@ __global__ void __launch_bounds__(256, 1) k_mc_lin_dense(McParams p, const float
         float* stv = p.part_stats + ((size_t)m * p.n_chunks + c) * 4;
         stv[0] = m_run; stv[1] = l_run; stv[2] = sum_lp; stv[3] = 0.0f;
     }
+    fuse_arrive(p.fuse, m, smem);
 }
 
 }  // namespace dibs

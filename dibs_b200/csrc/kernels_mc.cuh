@@ -11,10 +11,9 @@
 // shared memory, and produces the node's log-prob and the column of x^T R that every gradient needs.
 #pragma once
 #include "common.cuh"
+#include "assemble.cuh"
 
 namespace dibs {
-
-enum { MC_THETA_HARD = 0, MC_Z_SCORE = 1, MC_Z_REPARAM = 2, MC_LP_ONLY = 3 };
 
 struct McParams {
     const float* z; int z_ld;            // particle latents, row stride (floats)
@@ -26,7 +25,6 @@ struct McParams {
     int d, k, n_obs, n_samples;
     int n_chunks, s_per_chunk, gpb;      // chunking of the MC axis; graphs per block-round
     int paired;                          // units are sample pairs (s, s + S/2)
-    int dense_v2; float* dense_scratch;  // k_mc_lin_dense experiment: [n_local][n_chunks][2][d*d] per-CTA scratch
     const float* x;                      // [N, d]
     const int32_t* mask;                 // [N, d] or null
     const StepState* st; int which_split; int partitionable;
@@ -46,6 +44,7 @@ struct McParams {
     float* part_acc; int acc_size;       // [n_local][n_chunks][acc_size]
     float* part_stats;                   // [n_local][n_chunks][4]: running max, sum exp, sum lp, -
     float* lp_out;                       // optional [n_local][S]
+    FuseAsm fuse;                        // step loop: the particle's last gradient CTA runs the assemble step
 };
 
 __device__ __forceinline__ float norm_logpdf_pre(float x, float loc, float sig2, float lognorm) {
@@ -95,7 +94,7 @@ struct SoftmaxRun {
 // LinearGaussian (linearGaussian.py:278-338)
 // ------------------------------------------------------------------------------------------
 template <int DMAX, int MODE>
-__global__ void __launch_bounds__(256) k_mc_lingauss(McParams p) {
+__global__ void __launch_bounds__(256) k_mc_lingauss(const __grid_constant__ McParams p) {
     extern __shared__ __align__(16) float smem[];
     constexpr bool HARD = (MODE == MC_THETA_HARD || MODE == MC_Z_SCORE);
     const int d = p.d, N = p.n_obs, gpb = p.gpb;
@@ -247,6 +246,7 @@ __global__ void __launch_bounds__(256) k_mc_lingauss(McParams p) {
         float* stv = p.part_stats + ((size_t)m * p.n_chunks + c) * 4;
         stv[0] = m_run; stv[1] = l_run; stv[2] = sum_lp; stv[3] = 0.0f;
     }
+    fuse_arrive(p.fuse, m, smem);
 }
 
 inline size_t mc_lingauss_smem(int d, int k, int n_obs, int gpb, int dmax, bool has_mask) {

@@ -206,7 +206,7 @@ __device__ __forceinline__ double bge_schur(const double* __restrict__ R, int d,
 }
 
 template <int DMAX, int MODE>
-__global__ void __launch_bounds__(256, (DMAX > 32 ? 1 : 2)) k_mc_bge(McParams p) {
+__global__ void __launch_bounds__(256, (DMAX > 32 ? 1 : 2)) k_mc_bge(const __grid_constant__ McParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int LINE = DMAX > 32 ? 64 : 32;
     constexpr int ACCN = (DMAX * DMAX + 255) / 256;                    // accumulator entries per thread
@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(256, (DMAX > 32 ? 1 : 2)) k_mc_bge(McParams p)
         float* stv = p.part_stats + ((size_t)m * p.n_chunks + c) * 4;
         stv[0] = sStat[0]; stv[1] = sStat[1]; stv[2] = sStat[2]; stv[3] = 0.0f;
     }
+    fuse_arrive(p.fuse, m, reinterpret_cast<float*>(smem_raw));
 }
 
 inline size_t mc_bge_smem(int d, int dmax, int cap_samples, bool r_shared) {

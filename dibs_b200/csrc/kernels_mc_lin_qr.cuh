@@ -49,7 +49,7 @@ __device__ __forceinline__ float entry_from_bits(uint32_t bits, float sa, bool f
 }
 
 template <int DMAX, int MODE>
-__global__ void __launch_bounds__(192, (DMAX <= 20 ? 2 : 1)) k_mc_lin_qr(McParams p, RTri<DMAX> R) {
+__global__ void __launch_bounds__(192, (DMAX <= 20 ? 2 : 1)) k_mc_lin_qr(const __grid_constant__ McParams p, const __grid_constant__ RTri<DMAX> R) {
     extern __shared__ __align__(16) float smem[];
     constexpr bool HARD = (MODE == MC_THETA_HARD || MODE == MC_Z_SCORE);
     constexpr int MAT = DMAX * DMAX;                   // all per-(i,j) tables use the compile-time stride DMAX
@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(192, (DMAX <= 20 ? 2 : 1)) k_mc_lin_qr(McParam
         float* stv = p.part_stats + ((size_t)m * p.n_chunks + c) * 4;
         stv[0] = m_run; stv[1] = l_run; stv[2] = sum_lp; stv[3] = 0.0f;
     }
+    fuse_arrive(p.fuse, m, smem);
 }
 
 inline size_t mc_lin_qr_smem(int dmax, int gpb) {

@@ -29,7 +29,7 @@ template <int DMAX> constexpr int nn_max_threads() { return DMAX <= 32 ? 256 : (
 
 // HC: compile-time hidden-layer width (the node-mean shuffles unroll), 0 = runtime width
 template <int DMAX, int MODE, int HC>
-__global__ void __launch_bounds__(nn_max_threads<DMAX>()) k_mc_nn(McParams p) {
+__global__ void __launch_bounds__(nn_max_threads<DMAX>()) k_mc_nn(const __grid_constant__ McParams p) {
     extern __shared__ __align__(16) float smem[];
     constexpr bool HARD = (MODE == MC_THETA_HARD || MODE == MC_Z_SCORE);
     constexpr int NP = DMAX / 2;                  // packed pairs per row
@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(nn_max_threads<DMAX>()) k_mc_nn(McParams p) {
         float* stv = p.part_stats + ((size_t)m * p.n_chunks + c) * 4;
         stv[0] = m_run; stv[1] = l_run; stv[2] = sum_lp; stv[3] = 0.0f;
     }
+    fuse_arrive(p.fuse, m, smem);
 }
 
 inline size_t mc_nn_smem(int d, int n_obs, int dmax, int H, bool has_mask) {

@@ -101,7 +101,7 @@ __device__ __forceinline__ void peer_store(const PeerPush& p, size_t off, float 
 
 // copy `n4` float4 (the rank's own rows, already at their final offset in the local buffer) into every peer, then
 // the last CTA to finish bumps the epoch and raises the flags.  n4 == 0: signal only.
-__global__ void __launch_bounds__(256) k_peer_push(PeerPush p, const float4* __restrict__ src, size_t off4, size_t n4) {
+static __global__ void __launch_bounds__(256) k_peer_push(PeerPush p, const float4* __restrict__ src, size_t off4, size_t n4) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += stride) {
         const float4 v = src[off4 + e];
@@ -113,6 +113,6 @@ __global__ void __launch_bounds__(256) k_peer_push(PeerPush p, const float4* __r
 }
 
 // stand-alone wait (call-level "done" barrier at the start of dibs_svgd_steps)
-__global__ void k_peer_wait(PeerWait w) { peer_wait(w); }
+static __global__ void k_peer_wait(PeerWait w) { peer_wait(w); }
 
 }  // namespace dibs

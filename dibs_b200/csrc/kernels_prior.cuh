@@ -9,8 +9,10 @@
 #pragma once
 #include "common.cuh"
 #include "kernels_peer.cuh"
+#include "assemble.cuh"
 
 namespace dibs {
+
 
 // ------------------------------------------------------------------------------------------
 // step prologue: per particle, the raw scores U V^T (edge-probability pass, dibs.py:179-181) and the sub-keys of
@@ -65,6 +67,7 @@ struct AcycParams {
     const uint32_t* keys_override; int t_override;
     float alpha_linear, tau;
     float* ds_out;                       // [n_local][d*d]: sum over samples of dh/dS (before the 1/A mean)
+    FuseAsm fuse;                        // step loop: the particle's last gradient CTA runs the assemble step
 };
 
 // C = A * B for d x d row-major matrices with leading dimension ld, cooperatively by a group of threads.
@@ -81,7 +84,7 @@ __device__ __forceinline__ void group_matmul(const float* __restrict__ A, const 
 // One group (a warp when WARP_GROUP, else the whole CTA) handles one soft-graph sample at a time:
 // G = sigmoid(tau (eps + alpha S)); E = (I + G/d)^(d-1); dS += E^T o tau alpha G (1-G)   
 template <bool WARP_GROUP>
-__global__ void __launch_bounds__(256) k_acyclic_grad(AcycParams p) {
+__global__ void __launch_bounds__(256) k_acyclic_grad(const __grid_constant__ AcycParams p) {
     extern __shared__ __align__(16) float smem[];
     const int d = p.d, k = p.k, ld = d | 1;   // odd leading dimension: conflict-free column walks
     const int m = blockIdx.x, tid = threadIdx.x;
@@ -160,6 +163,7 @@ __global__ void __launch_bounds__(256) k_acyclic_grad(AcycParams p) {
         for (int g = 0; g < n_groups; ++g) sum += smem[d * d + 2 * d * k + (size_t)g * 6 * mat + 5 * mat + i * ld + j];
         out[e] = sum;
     }
+    fuse_arrive(p.fuse, m, smem);
 }
 
 inline size_t acyclic_smem(int d, int k, int n_groups) {
@@ -268,197 +272,13 @@ __global__ void __launch_bounds__(256) k_summary_reduce(const float* p_all, cons
 }
 
 // ------------------------------------------------------------------------------------------
-// assemble: partials -> d log p / dZ (and d/dTheta) for one particle
+// assemble: partials -> d log p / dZ (and d/dTheta) for one particle.  Hooks: one CTA per particle runs the
+// assemble step (assemble.cuh); the step loop runs it inside the gradient kernels (fuse_arrive)
 // ------------------------------------------------------------------------------------------
-struct AsmParams {
-    const float* z; int z_ld;
-    const float* scores;                  // [n_local][d*d] raw U V^T (k_prologue)
-    int n_local, d, k;
-    const StepState* st; int t_override;
-    float alpha_linear, beta_linear;
-    // Z-likelihood partials
-    const float* zacc; const float* zstats; int z_chunks; int z_mode;   // MC_Z_SCORE / MC_Z_REPARAM; zacc null = skip
-    int n_samples;
-    float sf_coef;                        // score_function_baseline
-    const float* baselines_in; float* baselines_out;
-    // theta partials
-    const float* thacc; const float* thstats; int th_chunks; int th_dim;
-    // prior
-    const float* acyc; int n_acyc;        // [n_local][acyc_chunks][d*d] sums over A samples; null = skip prior terms entirely
-    int acyc_chunks;
-    int constraint_only;                  // hook: return mean_a grad h alone (no beta, no other terms)
-    int prior_kind; float er_coef;        // log p - log(1-p)
-    float sigma_z2;                       // latent_prior_std ** 2
-    float* grad_z; int gz_ld;
-    float* grad_th; int gth_ld;
-    // next step's loop state and per-pass sub-keys (step loop only; null: skip)
-    uint32_t* next_keys; StepState* st_next;
-    int n_step_splits, n_particles, partitionable, m_offset; uint32_t pre_split_mask;
-    // peer-memory exchange fused into the kernel: every gradient value is also stored into the same row of each
-    // peer's gradient buffer, the last CTA raises the flags (push.world == 0: off)
-    PeerPush push;
-};
-
-// merged softmax normaliser of the chunk partials: weights w_c = exp(m_c - max) / sum_c l_c exp(m_c - max) into sW[c]
-// (one warp; chunks <= 32 handled by lanes, more by a strided loop), and sum of log-probs into *sum_lp
-__device__ __forceinline__ void merge_stats_warp(const float* __restrict__ stats, int chunks, float* sW, float* sum_lp,
-                                                 int lane) {
-    float mx = -INFINITY;
-    for (int c = lane; c < chunks; c += 32) mx = fmaxf(mx, stats[c * 4]);
-    mx = warp_max(mx);
-    float l = 0.0f, sl = 0.0f;
-    for (int c = lane; c < chunks; c += 32) {
-        const float mc = stats[c * 4];
-        const float w = (mc == -INFINITY) ? 0.0f : expf(mc - mx);
-        sW[c] = w;
-        l += stats[c * 4 + 1] * w;
-        sl += stats[c * 4 + 2];
-    }
-    // fixed-order (butterfly) sums: deterministic
-    l = warp_sum(l); sl = warp_sum(sl);
-    __syncwarp();
-    for (int c = lane; c < chunks; c += 32) sW[c] = sW[c] / l;
-    if (lane == 0) *sum_lp = sl;
-}
-
-// Latency-bound by construction (one CTA per particle, a few KB of inputs): every global read is issued as early as
-// possible and branch-free so the loads of a phase overlap; the serial threefry chains of the NEXT step's sub-keys
-// run on an otherwise idle warp underneath.
-__global__ void __launch_bounds__(256) k_assemble_grad(AsmParams p) {
+__global__ void __launch_bounds__(256) k_assemble_grad(const __grid_constant__ AsmParams p) {
     extern __shared__ __align__(16) float smem[];
-    const int d = p.d, k = p.k, dd = d * d, tid = threadIdx.x, m = blockIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int t = p.st ? p.st->t : p.t_override;
-    const float alpha = p.alpha_linear * (float)t;
-    const float beta = p.beta_linear * (float)t;
-    float* sZ = smem;                 // [2dk]
-    float* sP = sZ + 2 * d * k;       // [d*d]
-    float* sDS = sP + dd;             // [d*d]
-    float* sCol = sDS + dd;           // [d]
-    float* sWz = sCol + d;            // [z_chunks]
-    float* sWt = sWz + p.z_chunks;    // [th_chunks]
-    float* sMisc = sWt + p.th_chunks; // [2] sum of z log-probs, sum of theta log-probs
-
-    // ---- phase A: stage Z and the edge probabilities; warp 0/1 merge the softmax statistics; warp 7 derives keys
-    const float* zrow = p.z + (size_t)m * p.z_ld;
-    for (int e = tid; e < 2 * d * k; e += blockDim.x) sZ[e] = zrow[e];
-    for (int e = tid; e < dd; e += blockDim.x) {
-        const int i = e / d, j = e - i * d;
-        sP[e] = (i == j) ? 0.0f : sigmoidf_ref(alpha * p.scores[(size_t)m * dd + e]);
-    }
-    if (warp == 0 && p.zacc) merge_stats_warp(p.zstats + (size_t)m * p.z_chunks * 4, p.z_chunks, sWz, sMisc, lane);
-    if (warp == 1 && p.thacc) merge_stats_warp(p.thstats + (size_t)m * p.th_chunks * 4, p.th_chunks, sWt, sMisc + 1, lane);
-    if (warp == 7 && p.next_keys) {
-        // loop state: key <- after this step's (M+1)-way splits, t <- t + 1 (svgd.py:245,251,272); the sub-keys of
-        // the next step (svgd.py:245,251 / 695,699,703 and the pre-draw splits dibs.py:350,430) for this particle
-        uint2 key = make_uint2(p.st->key[0], p.st->key[1]);
-        for (int w = 0; w < p.n_step_splits; ++w) key = jax_split_row(key, 0u, (uint32_t)p.n_particles + 1u, p.partitionable != 0);
-        if (lane < p.n_step_splits) {
-            uint2 sk = key;
-            for (int w = 0; w < lane; ++w) sk = jax_split_row(sk, 0u, (uint32_t)p.n_particles + 1u, p.partitionable != 0);
-            sk = jax_split_row(sk, (uint32_t)(p.m_offset + m) + 1u, (uint32_t)p.n_particles + 1u, p.partitionable != 0);
-            if ((p.pre_split_mask >> lane) & 1u) sk = jax_split_row(sk, 1u, 2u, p.partitionable != 0);
-            uint32_t* o = p.next_keys + ((size_t)lane * p.n_local + m) * 2;
-            o[0] = sk.x; o[1] = sk.y;
-        }
-        if (m == 0 && lane == 0) {
-            p.st_next->key[0] = key.x; p.st_next->key[1] = key.y;
-            p.st_next->t = t + 1; p.st_next->pad = 0;
-        }
-    }
-    __syncthreads();
-    if (p.acyc && !p.constraint_only && p.prior_kind == 1) {
-        if (tid < d) {
-            float indeg = 0.0f;
-            for (int i = 0; i < d; ++i) indeg += sP[i * d + tid];        // soft_g.sum(0)  (graph.py:195)
-            sCol[tid] = -3.0f / (1.0f + indeg);
-        }
-        __syncthreads();
-    }
-    const float base_fac = (p.zacc && p.z_mode == MC_Z_SCORE && p.sf_coef > 0.0f) ? expf(-p.baselines_in[m]) : 1.0f;
-    // ---- phase B: dS
-    const float inv_acyc = 1.0f / (float)p.n_acyc;
-    for (int e = tid; e < dd; e += blockDim.x) {
-        const int i = e / d, j = e - i * d;
-        float w = 0.0f, acs = 0.0f;
-        if (p.zacc) {
-            const float* za = p.zacc + (size_t)m * p.z_chunks * dd + e;
-            for (int c = 0; c < p.z_chunks; ++c) w = fmaf(za[(size_t)c * dd], sWz[c], w);
-        }
-        if (p.acyc) {
-            const float* ac = p.acyc + (size_t)m * p.acyc_chunks * dd + e;
-            for (int c = 0; c < p.acyc_chunks; ++c) acs += ac[(size_t)c * dd];
-        }
-        float ds = 0.0f;
-        if (i != j) {
-            const float pe = sP[e];
-            // score: e^{-b} alpha (Gbar - P) (App. B-1/2; dibs.py:363-382); reparam: softmax-weighted dS
-            if (p.zacc) ds += (p.z_mode == MC_Z_SCORE) ? base_fac * alpha * (w - pe) : w;
-            if (p.acyc) {
-                const float acm = acs * inv_acyc;                                  // .mean(0)  (dibs.py:601)
-                if (p.constraint_only) ds += acm;
-                else {
-                    ds -= beta * acm;
-                    const float coef = p.prior_kind == 0 ? p.er_coef : (p.prior_kind == 1 ? sCol[j] : 0.0f);
-                    ds += coef * alpha * pe * (1.0f - pe);                          // App. B-5
-                }
-            }
-        }
-        sDS[e] = ds;
-    }
-    // theta gradient: softmax-weighted partial sums (dibs.py:531-549); independent of the barrier below
-    if (p.thacc) {
-        float* gth = p.grad_th + (size_t)m * p.gth_ld;
-        const float* ta = p.thacc + (size_t)m * p.th_chunks * p.th_dim;
-        for (int e = tid; e < p.th_dim; e += blockDim.x) {
-            float num = 0.0f;
-            for (int c = 0; c < p.th_chunks; ++c) num = fmaf(ta[(size_t)c * p.th_dim + e], sWt[c], num);
-            gth[e] = num;
-        }
-    }
-    __syncthreads();
-    // ---- phase C: chain rule through S = U V^T: dU = dS V, dV = dS^T U; Gaussian prior -Z/sigma^2 (dibs.py:657)
-    float* gz = p.grad_z + (size_t)m * p.gz_ld;
-    const bool gauss = p.acyc && !p.constraint_only;
-    for (int e = tid; e < d * k; e += blockDim.x) {
-        const int i = e / k, kk = e - i * k;
-        float du = 0.0f, dv = 0.0f;
-        for (int j = 0; j < d; ++j) {
-            const float2 zj = *reinterpret_cast<const float2*>(&sZ[(j * k + kk) * 2]);
-            du = fmaf(sDS[i * d + j], zj.y, du);
-            dv = fmaf(sDS[j * d + i], zj.x, dv);
-        }
-        if (gauss) {
-            du -= sZ[2 * e] / p.sigma_z2;
-            dv -= sZ[2 * e + 1] / p.sigma_z2;
-        }
-        gz[2 * e] = du; gz[2 * e + 1] = dv;
-    }
-    if (p.zacc && p.baselines_out && tid == 0) {
-        const float b_in = p.baselines_in ? p.baselines_in[m] : 0.0f;
-        // dibs.py:388-389 (only the score estimator touches the baseline)
-        p.baselines_out[m] = (p.z_mode == MC_Z_SCORE)
-            ? p.sf_coef * (sMisc[0] / (float)p.n_samples) + (1.0f - p.sf_coef) * b_in : b_in;
-    }
-    if (p.push.world) {
-        // fused exchange: the finished gradient row [dZ | dTheta] (just written, L1/L2-hot) goes to the same row of
-        // every peer's buffer as 128-bit stores (rows are 16-byte aligned, stride a multiple of 4 floats)
-        __syncthreads();
-        const size_t row4 = (size_t)(p.m_offset + m) * p.gz_ld / 4;
-        const float4* src = reinterpret_cast<const float4*>(gz);
-        for (int e = tid; e < p.gz_ld / 4; e += blockDim.x) {
-            const float4 v = __ldcg(src + e);
-#pragma unroll 1
-            for (int q = 0; q < p.push.world; ++q)
-                if (q != p.push.rank) reinterpret_cast<float4*>(p.push.dst[q])[row4 + e] = v;
-        }
-        peer_signal(p.push, gridDim.x);
-    }
+    assemble_particle(p, blockIdx.x, smem);
 }
-
-inline size_t assemble_smem(int d, int k, int z_chunks, int th_chunks) {
-    return ((size_t)2 * d * k + 2 * (size_t)d * d + d + z_chunks + th_chunks + 4) * sizeof(float);
-}
-
 
 // edge_probs / particle_to_g_lim hooks (dibs.py:84-99,168-184); one CTA per particle
 __global__ void __launch_bounds__(256) k_edge_probs(const float* z, int z_ld, int d, int k, float alpha,

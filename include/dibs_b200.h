@@ -133,14 +133,16 @@ int dibs_svgd_steps(dibs_plan* plan, int32_t t_start, int32_t n_steps, float* z,
 enum {
     DIBS_PHASE_MC_THETA = 0,    /* grad_theta estimator pass  (dibs.py:488-551)              */
     DIBS_PHASE_MC_Z = 1,        /* grad_z likelihood pass     (dibs.py:325-459)              */
-    DIBS_PHASE_ACYCLIC = 2,     /* grad_constraint_gumbel     (dibs.py:576-601)              */
-    DIBS_PHASE_ASSEMBLE = 3,    /* chain rule + latent prior  (dibs.py:626-658)              */
-    DIBS_PHASE_ALLGATHER = 4,   /* NCCL all-gather (multi-GPU only)                          */
-    DIBS_PHASE_PAIR_DIST = 5,   /* pairwise squared distances (kernel.py:30,66-71)           */
-    DIBS_PHASE_PAIR_KERNEL = 6, /* exp -> K                   (kernel.py:30,66-71)           */
-    DIBS_PHASE_PHI_UPDATE = 7,  /* phi partial sums per j slice (svgd.py:194-224,591-670)    */
-    DIBS_PHASE_STEP_KEYS = 8,   /* optimizer step + next step's raw scores U V^T (svgd.py:265,718-719; dibs.py:179-181);
-                                   the per-particle key splits (svgd.py:245,251,695,699,703) ride in the assemble kernel */
+    DIBS_PHASE_ACYCLIC = 2,     /* grad_constraint_gumbel     (dibs.py:576-601); in the step loop a particle's last
+                                   gradient CTA also runs the assemble step below (chain rule + latent prior + the
+                                   next step's key splits, dibs.py:626-658; svgd.py:245,251,695,699,703), so in the
+                                   serial per-kernel mode this phase carries it */
+    DIBS_PHASE_ASSEMBLE = 3,    /* (hooks only) stand-alone assemble kernel                  */
+    DIBS_PHASE_ALLGATHER = 4,   /* NCCL all-gather (multi-GPU fallback path only)            */
+    DIBS_PHASE_PAIR_DIST = 5,   /* pairwise squared distances -> K (kernel.py:30,66-71)      */
+    DIBS_PHASE_PAIR_KERNEL = 6, /* (unused: exp -> K is the epilogue of the distance kernel) */
+    DIBS_PHASE_PHI_UPDATE = 7,  /* phi + optimizer step + peer push (svgd.py:194-224,591-670,265,718-719) */
+    DIBS_PHASE_STEP_KEYS = 8,   /* next step's raw scores U V^T = the edge-probability pass (dibs.py:179-181) */
     DIBS_N_PHASES = 9
 };
 int dibs_svgd_steps_timed(dibs_plan* plan, int32_t t_start, int32_t n_steps, float* z, float* theta,

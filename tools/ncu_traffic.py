@@ -12,8 +12,8 @@ import statistics
 import subprocess
 import sys
 
-PHASE_OF = [("k_mc_", None), ("k_acyclic", "acyclic"), ("k_assemble_grad", "assemble"), ("k_pair_dist", "pair_dist"),
-            ("k_pair_finish", "pair_kernel"), ("k_phi_", "phi_update"), ("k_opt_update", "opt_update")]
+PHASE_OF = [("k_mc_", None), ("k_acyclic", "acyclic"), ("k_pair_dist", "pair_dist"), ("k_phi", "phi_update"),
+            ("k_prologue", "scores")]
 
 
 def main(rep, workload, out):
