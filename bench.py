@@ -46,6 +46,8 @@ WORKLOADS = {
     "c5": ("JointDiBS LinearGaussian n_vars=100 n_particles=4096 n_mc=128", "lingauss", 100, 4096, 128, 32, 0),
     "t_bge": ("MarginalDiBS BGe n_vars=20 n_particles=1024 n_mc=128 (north-star target shape)", "bge", 20, 1024, 128, 32, 0),
     "t_lin": ("JointDiBS LinearGaussian n_vars=20 n_particles=1024 n_mc=128 (north-star target shape)", "lingauss", 20, 1024, 128, 32, 0),
+    # diagnostics: per-rank gradient work of t_lin on 8 GPUs (128 particles per rank) reproduced on 2
+    "t_lin_q": ("JointDiBS LinearGaussian n_vars=20 n_particles=256 n_mc=128 (quarter of the target shape)", "lingauss", 20, 256, 128, 32, 0),
 }
 N_OBS = 100
 T_MID = 100          # time steps at mid-run t so alpha(t), beta(t) are non-degenerate (work per step is t-independent)
@@ -135,9 +137,8 @@ def kernel_work(name, m_loc, m_all):
     w["acyclic"] = dict(flops=m_loc * (a * nmat * 2 * d ** 3 + edge + 4 * d * d * k),
                         bytes=m_loc * 4 * (dz + d * d + 2 * dz + 2 * d * d + 2 * dth), bound="fp32")
     w["allgather"] = dict(flops=0, bytes=(m_all - m_loc) * 4 * 2 * dd, bound="nvlink")
-    # distances + exp -> K (one kernel: the tile's last feature-split CTA finishes the sum)
-    w["pair_dist"] = dict(flops=3 * m_loc * m_all * dd + 4 * m_loc * m_all,
-                          bytes=4 * (m_all * dd + m_loc * m_all * (3 if dth else 2)), bound="fp32")
+    w["pair_dist"] = dict(flops=3 * m_loc * m_all * dd, bytes=4 * (m_all * dd + m_loc * m_all), bound="fp32")
+    w["pair_kernel"] = dict(flops=4 * m_loc * m_all, bytes=4 * m_loc * m_all * (3 if dth else 2), bound="hbm")
     # phi + optimizer step (one kernel: the tile's last j-slice CTA finishes the sum and updates x, v)
     w["phi_update"] = dict(flops=2 * 2 * m_loc * m_all * dd + 8 * m_loc * dd,
                            bytes=4 * (2 * m_all * dd + 2 * m_loc * m_all + 6 * m_loc * dd), bound="fp32")
@@ -469,6 +470,13 @@ def measure_workload(ctx, name, K, W, n_prof, want_hot=True):
         roofline["step_bound_us"] = round(tb, 2)
         roofline["step_frac"] = round(tb / (total_ms / K * 1e3), 4)
         roofline["step_bound_by_kernel"] = per
+    if os.environ.get("DIBS_BENCH_TIMELINE") == "1":
+        # diagnostics: the step GRAPH replayed with an event node behind every kernel -> END time of each kernel
+        # relative to the step's start, concurrency and peer waits included (us, mean over 20 steps, this rank)
+        n_tl = 20
+        step_ms_tl, tl_ms = steps_timed(t, n_tl, per_kernel=2); t += n_tl
+        res["timeline_end_us"] = {ph: round(float(tl_ms[i]) / n_tl * 1e3, 1) for i, ph in enumerate(nat.PHASES) if tl_ms[i] > 0}
+        res["timeline_end_us"]["step"] = round(float(step_ms_tl.mean()) * 1e3, 1)
     res.update(kernels=kernels, roofline=roofline, model=model, t_next=t)
     return res
 
@@ -491,7 +499,7 @@ def pass_rooflines(ctx, name, res):
     m_loc = m // ctx.world
     out = {}
     kn = res["kernels"]
-    km_us = sum(kn[p]["us"] for p in ("pair_dist",) if p in kn)
+    km_us = sum(kn[p]["us"] for p in ("pair_dist", "pair_kernel") if p in kn)
     if km_us > 0:
         by = 4 * m * D + 4 * m_loc * m                      # read particles once, write K once
         fl = 3 * m_loc * m * D                              # difference form
@@ -499,7 +507,7 @@ def pass_rooflines(ctx, name, res):
                                 "gbs": round(by / km_us / 1e3, 2), "hbm_frac": round(by / km_us / 1e3 / hbm_peak, 4),
                                 "tflops": round(fl / km_us / 1e6, 3), "fp32_frac": round(fl / km_us / 1e6 / fp32_tf, 4),
                                 "bound": "fp32_simt (AI = %.0f flop/B >> ridge %.1f)" % (fl / by, fp32_tf * 1e3 / hbm_peak),
-                                "traffic": kn.get("pair_dist", {}).get("traffic")}
+                                "traffic": (kn.get("pair_dist", {}).get("traffic") or 0) + (kn.get("pair_kernel", {}).get("traffic") or 0) or None}
     model = res["model"]
     stream = torch.cuda.current_stream(ctx.device)
 
@@ -629,6 +637,7 @@ def run_native(args):
         "roofline": roofline,
         "kernels": res["kernels"],
         "also": also,
+        "timeline_end_us": res.get("timeline_end_us"),
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)

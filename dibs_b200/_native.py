@@ -63,8 +63,8 @@ PROTOTYPES = {
     "dibs_launch_count": (ctypes.c_int64, []),
 }
 
-# kernels of one step in the order of DIBS_PHASE_*; "assemble" and "pair_kernel" are hook-only since the assemble step
-# runs inside the gradient kernels and exp -> K inside the distance kernel ("acyclic" / "pair_dist" carry their time)
+# kernels of one step in the order of DIBS_PHASE_*; "assemble" is hook-only: in the step loop the assemble step runs
+# inside the gradient kernels (the serial per-kernel mode charges it to "acyclic")
 PHASES = ("mc_theta", "mc_z", "acyclic", "assemble", "allgather", "pair_dist", "pair_kernel", "phi_update", "scores")
 
 _lib = None

@@ -145,10 +145,12 @@ static __device__ __noinline__ void assemble_particle(const AsmParams& p, int m,
         float w = 0.0f, acs = 0.0f;
         if (p.zacc) {
             const float* za = p.zacc + (size_t)m * p.z_chunks * dd + e;
+#pragma unroll 8
             for (int c = 0; c < p.z_chunks; ++c) w = fmaf(__ldcg(za + (size_t)c * dd), sWz[c], w);
         }
         if (p.acyc) {
             const float* ac = p.acyc + (size_t)m * p.acyc_chunks * dd + e;
+#pragma unroll 4
             for (int c = 0; c < p.acyc_chunks; ++c) acs += __ldcg(ac + (size_t)c * dd);
         }
         float ds = 0.0f;
@@ -174,6 +176,7 @@ static __device__ __noinline__ void assemble_particle(const AsmParams& p, int m,
         const float* ta = p.thacc + (size_t)m * p.th_chunks * p.th_dim;
         for (int e = tid; e < p.th_dim; e += nthr) {
             float num = 0.0f;
+#pragma unroll 8
             for (int c = 0; c < p.th_chunks; ++c) num = fmaf(__ldcg(ta + (size_t)c * p.th_dim + e), sWt[c], num);
             gth[e] = num;
         }

@@ -155,7 +155,7 @@ struct dibs_plan {
     float* phi_part = nullptr;     // [n_jsplit][M_loc][D]
     // arrival counters of the in-kernel reductions (zero between launches): gradient CTAs per particle (fused
     // assemble), feature splits per K tile, j slices per phi tile
-    uint32_t *arrive = nullptr, *dist_cnt = nullptr, *phi_cnt = nullptr;
+    uint32_t *arrive = nullptr, *phi_cnt = nullptr;
     // CUDA graphs of one step, per buffer parity
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
     int kernels_per_step = 0;
@@ -175,10 +175,24 @@ struct dibs_plan {
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_phase;     // phase id of the work that ENDS at ev_pool[i]; -1 = start marker
     size_t ev_used = 0;
+    // timeline mode of dibs_svgd_steps_timed (per_kernel = 2): the step graph with an event behind every kernel
+    int tl_capture = -1;
+    cudaGraphExec_t tl_exec[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> tl_ev[2];
+    std::vector<int> tl_phase[2];
 };
 
 // mark the end of one kernel (phase) on `stream` when the plan is in timing mode
 static void mark(dibs_plan* p, cudaStream_t stream, int phase) {
+    if (p->tl_capture >= 0) {
+        // timeline mode: an external event-record node behind the kernel, on the branch the kernel runs on
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        cudaEventRecordWithFlags(e, stream, cudaEventRecordExternal);
+        p->tl_ev[p->tl_capture].push_back(e);
+        p->tl_phase[p->tl_capture].push_back(phase);
+        return;
+    }
     if (!p->timing) return;
     if (p->ev_used == p->ev_pool.size()) {
         cudaEvent_t e = nullptr;
@@ -235,7 +249,7 @@ static McShape mc_shape_for(bool qr, int likelihood, int d, int hidden, int n_lo
     if (qr) {
         const int Q = (S + 1) / 2;
         int best = 1; long best_cost = -1;
-        for (int g = 1; g * d <= 192 && g <= Q; ++g) {
+        for (int g = 1; g * d <= 192 && g <= Q && g <= 16; ++g) {       // <= 16 slots: 32 samples per warp-wide reduction
             long cost = (long)ceil_div(Q, g) * (((g * d) + 31) / 32 * 32);
             if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = g; }
         }
@@ -445,8 +459,7 @@ static int ensure_step_ws(dibs_plan* p) {
         return r;
     size_t plane = (size_t)p->M_loc * p->M * sizeof(float);
     if ((r = alloc((void**)&p->arrive, (size_t)p->M_loc * sizeof(uint32_t))) ||
-        (r = alloc((void**)&p->dist_cnt, (size_t)ceil_div(p->M, KT) * ceil_div(p->M_loc, KT) * sizeof(uint32_t))) ||
-        (r = alloc((void**)&p->phi_cnt, (size_t)(ceil_div(p->Dz, PT_C) + ceil_div(p->Dth, PT_C)) * ceil_div(p->M_loc, PB_I) * sizeof(uint32_t))) ||
+        (r = alloc((void**)&p->phi_cnt, (size_t)(ceil_div(p->Dz, PT_C) + ceil_div(p->Dth, PT_C)) * ceil_div(p->M_loc, 32) * sizeof(uint32_t))) ||
         (r = alloc((void**)&p->dist_part, plane * p->n_split)) || (r = alloc((void**)&p->kz, plane)) ||
         (r = alloc((void**)&p->kt, plane)) || (r = alloc((void**)&p->kfull, plane)) ||
         (r = alloc((void**)&p->phi_part, (size_t)p->n_jsplit * p->M_loc * p->D * sizeof(float))))
@@ -469,6 +482,7 @@ extern "C" int dibs_plan_status(dibs_plan* p) {
 extern "C" int dibs_plan_destroy(dibs_plan* p) {
     if (!p) return DIBS_OK;
     for (int i = 0; i < 2; ++i) if (p->gexec[i]) cudaGraphExecDestroy(p->gexec[i]);
+    for (int i = 0; i < 2; ++i) { if (p->tl_exec[i]) cudaGraphExecDestroy(p->tl_exec[i]); for (cudaEvent_t e : p->tl_ev[i]) cudaEventDestroy(e); }
     for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
     if (!p->ipc_opened.empty()) {
         cudaDeviceSynchronize();
@@ -490,7 +504,7 @@ extern "C" int dibs_plan_destroy(dibs_plan* p) {
     for (int i = 0; i < 3; ++i) { if (p->aux[i]) cudaStreamDestroy(p->aux[i]); if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]); }
     for (int i = 0; i < 2; ++i) if (p->ev_fork[i]) cudaEventDestroy(p->ev_fork[i]);
     if (p->peer_error) cudaFreeHost(p->peer_error);
-    void* ptrs[] = {p->summary_ws, p->arrive, p->dist_cnt, p->phi_cnt, p->rx_dense, p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->gk[0], p->gk[1], p->peer_flags_local, p->peer_epoch, p->peer_counter, p->v, p->base, p->st, p->step_keys, p->scores,
+    void* ptrs[] = {p->summary_ws, p->arrive, p->phi_cnt, p->rx_dense, p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->gk[0], p->gk[1], p->peer_flags_local, p->peer_epoch, p->peer_counter, p->v, p->base, p->st, p->step_keys, p->scores,
                     p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->dist_part, p->kz, p->kt, p->kfull, p->phi_part};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
@@ -846,7 +860,7 @@ static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_st
         q.part_acc = th_acc; q.acc_size = p->th_acc_size; q.part_stats = th_stats;
         q.fuse = fuse;
         TRY(launch_mc<MC_THETA_HARD>(p, q, sh, s_th));
-        mark(p, stream, DIBS_PHASE_MC_THETA);
+        mark(p, s_th, DIBS_PHASE_MC_THETA);
     }
     fill_mc(p, s, q);
     q.which_split = joint ? 1 : 0; q.keys_override = pass_keys(s, q.which_split);
@@ -856,7 +870,7 @@ static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_st
     else TRY(launch_mc<MC_Z_REPARAM>(p, q, sh, stream));
     mark(p, stream, DIBS_PHASE_MC_Z);
     TRY(launch_acyc(p, s, joint ? 2 : 1, acyc, s_ac, &fuse));
-    mark(p, stream, DIBS_PHASE_ACYCLIC);
+    mark(p, s_ac, DIBS_PHASE_ACYCLIC);
     if (conc) {
         if (joint) TRY(stream_edge(s_th, stream, p->ev_join[0]));
         TRY(stream_edge(s_ac, stream, p->ev_join[1]));
@@ -868,27 +882,33 @@ static void fill_pair(const dibs_plan* p, PairParams& q) {
     memset(&q, 0, sizeof(q));
     q.n_all = p->M; q.row0 = p->row0; q.n_rows = p->M_loc; q.dz = p->Dz; q.dth = p->Dth;
     q.n_split = p->n_split; q.n_split_z = p->n_split_z; q.split_len_z = p->split_len_z; q.split_len_t = p->split_len_t;
-    q.dist_part = p->dist_part; q.dist_cnt = p->dist_cnt;
+    q.dist_part = p->dist_part;
     q.kz = p->kz; q.kt = p->Dth ? p->kt : nullptr; q.kfull = p->kfull;
     q.h_z = p->cfg.h_latent; q.h_t = p->cfg.h_theta; q.scale_z = p->cfg.scale_latent; q.scale_t = p->cfg.scale_theta;
     q.n_jsplit = p->n_jsplit; q.j_len = p->j_len; q.phi_part = p->phi_part; q.phi_cnt = p->phi_cnt;
     q.optimizer = p->cfg.optimizer; q.stepsize = p->cfg.stepsize;
 }
 
-// kernel matrix of the rank's rows against all particles: squared distances per feature split, finished into
-// K_z, K_theta, K by each tile's last split CTA
+// kernel matrix of the rank's rows against all particles: squared distances per feature split, then exp -> K
 static int launch_kmat(dibs_plan* p, const PairParams& q, cudaStream_t stream) {
     dim3 g1(ceil_div(q.n_all, KT), ceil_div(q.n_rows, KT), q.n_split);
     k_pair_dist<<<g1, 256, 0, stream>>>(q);
     LAUNCHED();
     mark(p, stream, DIBS_PHASE_PAIR_DIST);
+    size_t plane = (size_t)q.n_rows * q.n_all;
+    int blocks = (int)((plane + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+    k_pair_finish<<<blocks, 256, 0, stream>>>(q);
+    LAUNCHED();
+    mark(p, stream, DIBS_PHASE_PAIR_KERNEL);
     return DIBS_OK;
 }
 
 // phi partial sums per j slice, finished (mean, optimizer step, peer push) by each tile's last slice CTA
 static int launch_phi(dibs_plan* p, const PairParams& q, cudaStream_t stream) {
-    dim3 gb(ceil_div(q.dz, PT_C) + ceil_div(q.dth, PT_C), ceil_div(q.n_rows, PB_I), q.n_jsplit);
-    k_phi<<<gb, 128, 0, stream>>>(q);
+    // 64-row tiles once a rank owns enough rows to fill the GPU with them, 32-row tiles below (twice the CTAs)
+    const int cols = ceil_div(q.dz, PT_C) + ceil_div(q.dth, PT_C);
+    if (q.n_rows >= 512) k_phi<8><<<dim3(cols, ceil_div(q.n_rows, 64), q.n_jsplit), 128, 0, stream>>>(q);
+    else k_phi<4><<<dim3(cols, ceil_div(q.n_rows, 32), q.n_jsplit), 128, 0, stream>>>(q);
     LAUNCHED();
     mark(p, stream, DIBS_PHASE_PHI_UPDATE);
     return DIBS_OK;
@@ -968,6 +988,7 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream, bool conc) {
     q.x_next = Pn + (size_t)p->row0 * p->ld; q.next_ld = p->ld;
     q.v = p->v; q.v_ld = p->D;
     if (fuse) fill_push(p, q.push_x, PEER_KIND_X, p->peer_pk[cur ^ 1]);
+    if (p->tl_capture >= 0) mark(p, stream, DIBS_PHASE_ASSEMBLE);     // timeline diagnostics: the join point before phi
     TRY(launch_phi(p, q, stream));
     // raw scores U V^T of the NEXT step from the updated latent rows (edge-probability pass, dibs.py:179-181)
     TRY(launch_prologue(p, q.x_next, p->ld, p->M_loc, p->row0, nullptr, nullptr, 0, 0u, p->scores, nullptr, stream));
@@ -1021,7 +1042,28 @@ static int svgd_steps_impl(dibs_plan* p, int32_t t_start, int32_t n_steps, float
 
     // peer-memory path: publish the rows this call just packed (later steps: the phi kernel pushes its updated rows)
     if (p->p2p) TRY(launch_push(p, PEER_KIND_X, p->pk[0], p->peer_pk[0], stream));
+    const bool timeline = timed && per_kernel == 2;
+    if (timeline) per_kernel = 0;
     const bool graph = p->use_graph && !(timed && per_kernel);
+    if (timeline && !p->tl_exec[0]) {
+        for (int par = 0; par < 2; ++par) {
+            cudaGraph_t g = nullptr;
+            if (!p->cap_stream) CU(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+            long long before = g_launches.load();
+            CU(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
+            p->tl_capture = par;
+            mark(p, p->cap_stream, -1);
+            int r = enqueue_step(p, par, p->cap_stream, p->concurrent);
+            p->tl_capture = -1;
+            cudaError_t e = cudaStreamEndCapture(p->cap_stream, &g);
+            g_launches.store(before);
+            if (r != DIBS_OK) { if (g) cudaGraphDestroy(g); return r; }
+            if (e != cudaSuccess) return fail(DIBS_ERR_CUDA, std::string("cudaStreamEndCapture (timeline): ") + cudaGetErrorString(e));
+            CU(cudaGraphInstantiate(&p->tl_exec[par], g, 0));
+            cudaGraphDestroy(g);
+        }
+    }
+    if (timeline && phase_ms) for (int i = 0; i < DIBS_N_PHASES; ++i) phase_ms[i] = 0.0f;
     p->ev_used = 0;
     if (graph && !p->gexec[0]) {
         if (p->cfg.world_size > 1 && !p->p2p) {
@@ -1069,7 +1111,22 @@ static int svgd_steps_impl(dibs_plan* p, int32_t t_start, int32_t n_steps, float
             mark(p, stream, -1);
             p->timing = per_kernel != 0;
         }
-        if (graph) {
+        if (timeline) {
+            // one step at a time: the events of a parity graph are re-recorded by its next launch
+            CU(cudaGraphLaunch(p->tl_exec[cur], stream));
+            g_launches.fetch_add(p->kernels_per_step, std::memory_order_relaxed);
+            CU(cudaStreamSynchronize(stream));
+            float last = 0.0f;
+            for (size_t e = 1; e < p->tl_ev[cur].size(); ++e) {
+                float ms = 0.0f;
+                CU(cudaEventElapsedTime(&ms, p->tl_ev[cur][0], p->tl_ev[cur][e]));
+                const int ph = p->tl_phase[cur][e];
+                if (phase_ms && ph >= 0 && ph < DIBS_N_PHASES) phase_ms[ph] += ms;      // END time of the phase's kernel
+                if (ms > last) last = ms;
+            }
+            if (step_ms) step_ms[i] = last;
+            continue;
+        } else if (graph) {
             CU(cudaGraphLaunch(p->gexec[cur], stream));
             g_launches.fetch_add(p->kernels_per_step, std::memory_order_relaxed);
         } else {
@@ -1078,7 +1135,7 @@ static int svgd_steps_impl(dibs_plan* p, int32_t t_start, int32_t n_steps, float
         if (timed && !per_kernel) { p->timing = true; mark(p, stream, DIBS_N_PHASES); }
         p->timing = false;
     }
-    if (timed) {
+    if (timed && !timeline) {
         // device time between consecutive events on the launching stream; a -1 marker starts a step
         if (phase_ms) for (int i = 0; i < DIBS_N_PHASES; ++i) phase_ms[i] = 0.0f;
         CU(cudaStreamSynchronize(stream));
@@ -1116,7 +1173,7 @@ extern "C" int dibs_svgd_steps_timed(dibs_plan* p, int32_t t_start, int32_t n_st
                                      int32_t per_kernel, void* l2_flush_buf, int64_t l2_flush_bytes,
                                      float* step_ms_host, float* phase_ms_host) {
     if (!step_ms_host && !phase_ms_host) return fail(DIBS_ERR_INVALID_ARG, "dibs_svgd_steps_timed: no output buffer");
-    if (phase_ms_host && !per_kernel) return fail(DIBS_ERR_INVALID_ARG, "phase_ms_host needs per_kernel = 1");
+    if (phase_ms_host && !per_kernel) return fail(DIBS_ERR_INVALID_ARG, "phase_ms_host needs per_kernel = 1 or 2");
     if (l2_flush_buf && l2_flush_bytes <= 0) return fail(DIBS_ERR_INVALID_ARG, "l2_flush_bytes must be positive");
     return svgd_steps_impl(p, t_start, n_steps, z, theta, v_z, v_theta, key, sf_baseline, stream, true, per_kernel,
                            l2_flush_buf, (size_t)(l2_flush_buf ? l2_flush_bytes : 0), step_ms_host, phase_ms_host);
@@ -1428,10 +1485,10 @@ static int hook_pair(dibs_plan* p, const float* z, const float* theta, const flo
     fill_pair(p, q);
     q.n_all = n; q.row0 = 0; q.n_rows = n;
     size_t plane = (size_t)n * n;
-    const size_t n_cnt = (size_t)ceil_div(n, KT) * ceil_div(n, KT) + (size_t)(ceil_div(p->Dz, PT_C) + ceil_div(p->Dth, PT_C)) * ceil_div(n, PB_I);
+    const size_t n_cnt = (size_t)(ceil_div(p->Dz, PT_C) + ceil_div(p->Dth, PT_C)) * ceil_div(n, 32);
     TRY(sc.get(&cnt, n_cnt));
     CU(cudaMemsetAsync(cnt, 0, n_cnt * sizeof(uint32_t), stream));
-    q.dist_cnt = cnt; q.phi_cnt = cnt + (size_t)ceil_div(n, KT) * ceil_div(n, KT);
+    q.phi_cnt = cnt;
     TRY(sc.get(&dist, plane * p->n_split));
     TRY(sc.get(&kz, plane)); TRY(sc.get(&kt, plane));
     if (!k_out) TRY(sc.get(&kf, plane)); else kf = k_out;

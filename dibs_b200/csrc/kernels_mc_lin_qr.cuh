@@ -12,11 +12,13 @@
 // Two d x d triangular mat-vecs per (graph, node) -- d^2 FMAs instead of 2 N d -- with the SAME conditioning
 // as the reference's direct form (a sum of squares of one fp32 mat-vec; no Gram-matrix cancellation).
 //
-// Work decomposition: CTA = (particle, chunk of sample PAIRS).  Per round the CTA first draws the entries of
-// gpb graph pairs into shared memory with a flat thread mapping, then thread = (pair q, node j) owns the
-// columns j of the two graphs s = q and s = q + S/2: in JAX's legacy threefry layout those two draws are the
-// two lanes of ONE threefry block (counter pair (e, e + n/2)), so no random bits are thrown away.  (Host side:
-// odd S or the partitionable PRNG layout fall back to k_mc_lingauss, which draws one entry per block.)
+// Work decomposition: CTA = (particle, chunk of sample PAIRS); thread = (pair q, node j) owns the columns j of the
+// two graphs s = q and s = q + S/2 from the draw to the accumulation: in JAX's legacy threefry layout those two
+// draws are the two lanes of ONE threefry block (counter pair (e, e + n/2)), so no random bits are thrown away, and
+// a thread draws exactly the entries it consumes -- into registers, nothing is staged for other threads.  The only
+// cross-thread step of a round is the sum of the d node log-probs of a sample: ONE barrier per round, after which
+// every warp redoes the (tiny) per-sample reduction and softmax bookkeeping for itself.  (Host side: odd S or the
+// partitionable PRNG layout fall back to k_mc_lingauss, which draws one entry per block.)
 // Rx lives in the kernel-parameter constant bank: with the mat-vec loops fully unrolled every FMA takes its
 // Rx operand from a uniform register (LDCU), no shared-memory traffic at all in the inner loops.
 #pragma once
@@ -48,26 +50,34 @@ __device__ __forceinline__ float entry_from_bits(uint32_t bits, float sa, bool f
     return sigmoidf_ref(tau * ((logf(u) - log1pf(-u)) + sa));
 }
 
+// shared-memory strides: thread (slot, j) owns PRIVATE columns of the per-slot tables (stride-DMAX walks down a
+// column); a slot stride congruent to d (mod 32) makes the bank of such an access equal to the flat thread index
+__host__ __device__ inline int qr_pad_stride(int base, int d) { return base + ((d - base) % 32 + 32) % 32; }
+
 template <int DMAX, int MODE>
-__global__ void __launch_bounds__(192, (DMAX <= 20 ? 2 : 1)) k_mc_lin_qr(const __grid_constant__ McParams p, const __grid_constant__ RTri<DMAX> R) {
+__global__ void __launch_bounds__(192, (DMAX <= 20 ? 3 : 1))
+k_mc_lin_qr(const __grid_constant__ McParams p, const __grid_constant__ RTri<DMAX> R) {
     extern __shared__ __align__(16) float smem[];
     constexpr bool HARD = (MODE == MC_THETA_HARD || MODE == MC_Z_SCORE);
     constexpr int MAT = DMAX * DMAX;                   // all per-(i,j) tables use the compile-time stride DMAX
-    const int d = p.d, dd = d * d, gpb = p.gpb;        // gpb = sample pairs ("slots") per round
-    const int m = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+    constexpr int NS = DMAX + 1;                       // odd row stride of the node log-prob table
+    constexpr int IL = 4;                              // independent threefry chains per thread
+    static_assert(DMAX % IL == 0 && DMAX <= 32, "row batches of 4; one bit per row in the hard-graph masks");
+    const int d = p.d, dd = d * d, gpb = p.gpb;        // gpb = sample pairs ("slots") per round, <= 16
+    const int m = blockIdx.x, c = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const int t = p.st ? p.st->t : p.t_override;
     const int S = p.n_samples, Qh = (S + 1) >> 1;      // slot q holds samples q and q + Qh
+    const int acc_stride = qr_pad_stride(MAT, d), g_stride = qr_pad_stride(2 * MAT, d);
 
     float* sA = smem;                       // [MAT] hard: P_ij; soft tau==1: exp(-alpha s_ij); soft: alpha s_ij
     float* sTh = sA + MAT;                  // [MAT] theta_ij
     float* sLpTh = sTh + MAT;               // [MAT] logN(theta_ij; mean_edge, sig_edge)
-    float* sAccAll = sLpTh + MAT;           // [gpb][MAT] softmax-weighted running sums, one private column per thread
-    float* sGall = sAccAll + gpb * MAT;     // [gpb][2][MAT] graph entries of the current round
-    float* sNode = sGall + 2 * gpb * MAT;   // [2*gpb][DMAX] per-node log-probs
-    float* sLpS = sNode + 2 * gpb * DMAX;   // [2*gpb] per-sample log-probs
-    float* sStat = sLpS + 2 * gpb;          // [4] round max, sum exp, sum lp
+    float* sAccAll = sLpTh + MAT;           // [gpb][acc_stride] softmax-weighted running sums, one private column per thread
+    float* sGall = sAccAll + gpb * acc_stride;      // [gpb][g_stride] soft graph entries of the round (private columns)
+    float* sNode = sGall + gpb * g_stride;  // [2][2*gpb][NS] per-node log-probs, double-buffered by round parity
 
-    const bool use_ext = p.g_ext != nullptr;
+    // caller-supplied graphs exist for the log-prob hook only (dibs_log_joint_prob): a compile-time false elsewhere
+    const bool use_ext = (MODE == MC_LP_ONLY) && p.g_ext != nullptr;
     const bool fast_soft = !HARD && !use_ext && p.tau == 1.0f;
     const float alpha = p.alpha_linear * (float)t;     // dibs.py:70: fp32 product of slope and step
     {
@@ -94,9 +104,10 @@ __global__ void __launch_bounds__(192, (DMAX <= 20 ? 2 : 1)) k_mc_lin_qr(const _
     const int q_end = min(Qh, q_begin + p.s_per_chunk);
     const float inv_s2 = 1.0f / p.s2, inv_se2 = 1.0f / p.sig2_edge;
     const uint32_t half = ((uint32_t)S * dd) >> 1;
-    const float inv_dd = 1.0f / (float)dd, inv_d = 1.0f / (float)d;
+    const float cst = (float)p.n_obs * p.log2pis2;
 
-    float* sAcc = sAccAll + slot * MAT + j;            // sAcc[i*DMAX]
+    float* sAcc = sAccAll + (active ? slot : 0) * acc_stride + j;     // sAcc[i*DMAX]
+    float* sG = sGall + (active ? slot : 0) * g_stride + j;           // sG[g*MAT + i*DMAX]
     if (active && MODE != MC_LP_ONLY) {
 #pragma unroll
         for (int i = 0; i < DMAX; ++i) sAcc[i * DMAX] = 0.0f;
@@ -104,211 +115,169 @@ __global__ void __launch_bounds__(192, (DMAX <= 20 ? 2 : 1)) k_mc_lin_qr(const _
     float m_run = -INFINITY, l_run = 0.0f, sum_lp = 0.0f;
     __syncthreads();
 
-    for (int q0 = q_begin; q0 < q_end; q0 += gpb) {
-        // ---- phase 1: all threads draw the round's graph entries into shared memory (flat, coalesced)
-        const int n_draw = gpb * dd;
-        constexpr int IL = 4;                  // independent threefry chains per thread
-        for (int idx0 = tid; idx0 < n_draw; idx0 += IL * blockDim.x) {
-            uint32_t x0[IL], x1[IL];
-            int off[IL];                       // destination in sGall, or -1
-            float sa[IL];
-            bool draw[IL];
-#pragma unroll
-            for (int u = 0; u < IL; ++u) {
-                const int idx = idx0 + u * blockDim.x;
-                // idx -> (slot, i, j) without integer division (idx < 2^14: the float quotients are exact after +0.5)
-                const int sl = __float2int_rz(((float)idx + 0.5f) * inv_dd), ij = idx - sl * dd;
-                const int i = __float2int_rz(((float)ij + 0.5f) * inv_d), jj = ij - i * d;
-                const int qq = q0 + sl;
-                const bool in = idx < n_draw;
-                off[u] = in ? (2 * sl) * MAT + i * DMAX + jj : -1;
-                // zero_diagonal (utils/func.py:117-125): diagonal draws are discarded
-                draw[u] = in && qq < q_end && i != jj;
-                // legacy threefry layout, S even: flat elements e0 and e0 + n/2 are the two lanes of one block
-                const uint32_t e0 = (uint32_t)qq * dd + ij;
-                x0[u] = e0; x1[u] = e0 + half;
-                sa[u] = draw[u] ? sA[i * DMAX + jj] : 0.0f;
-                if (use_ext) {
-                    float ga = 0.0f, gb = 0.0f;
-                    if (draw[u]) {
-                        ga = p.g_ext[((size_t)m * S + qq) * dd + ij];
-                        if (qq + Qh < S) gb = p.g_ext[((size_t)m * S + qq + Qh) * dd + ij];
-                    }
-                    x0[u] = __float_as_uint(ga); x1[u] = __float_as_uint(gb);
-                }
-            }
-            if (!use_ext) threefry2x32_n<IL>(key.x, key.y, x0, x1);
-#pragma unroll
-            for (int u = 0; u < IL; ++u) {
-                if (off[u] < 0) continue;
-                float ga, gb;
-                if (use_ext) { ga = __uint_as_float(x0[u]); gb = __uint_as_float(x1[u]); }
-                else {
-                    ga = draw[u] ? entry_from_bits<HARD>(x0[u], sa[u], fast_soft, p.tau) : 0.0f;
-                    gb = draw[u] ? entry_from_bits<HARD>(x1[u], sa[u], fast_soft, p.tau) : 0.0f;
-                }
-                sGall[off[u]] = ga; sGall[off[u] + MAT] = gb;
-            }
-        }
-        __syncthreads();
-        // ---- phase 2: thread (slot, j) owns column j of the two graphs of its slot
+    int buf = 0;
+    for (int q0 = q_begin; q0 < q_end; q0 += gpb, buf ^= 1) {
+        // ---- draw: thread (slot, j) draws column j of the two graphs of its slot (and nothing else).  In JAX's
+        // legacy threefry layout flat elements e and e + n/2 -- samples q and q + S/2 -- are the two lanes of ONE block.
         const int q = q0 + slot;
         const bool v0 = active && q < q_end;
         const bool v1 = v0 && q + Qh < S;
-        const float* sG0 = sGall + (2 * slot) * MAT + j;     // sG0[i*DMAX] = G_s0[i][j]
-        const float* sG1 = sG0 + MAT;
-        float u0[DMAX], u1[DMAX];
         float prior0 = 0.0f, prior1 = 0.0f;
+        uint32_t gm0 = 0u, gm1 = 0u;                   // hard graphs: bit i = G[i][j]
+        uint32_t e_row = (uint32_t)q * dd + j;         // flat index of entry (i, j) of sample q, row by row
+        // a ROLLED loop over batches of IL rows (IL independent threefry chains in flight): the entries go to the
+        // hard-graph masks or to the thread's private shared-memory column, so nothing but the two priors stays live
+#pragma unroll 1
+        for (int i0 = 0; i0 < DMAX; i0 += IL) {
+            uint32_t x0[IL], x1[IL];
+            if (use_ext) {
 #pragma unroll
-        for (int i = 0; i < DMAX; ++i) {
-            float ga = 0.0f, gb = 0.0f, th = 0.0f;
-            if (v0 && i < d) {
-                ga = sG0[i * DMAX]; gb = sG1[i * DMAX];
-                th = sTh[i * DMAX + j];
-                // log p(theta | G): sum g * logN(theta; mean_edge, sig_edge)   (linearGaussian.py:289)
-                const float lpth = sLpTh[i * DMAX + j];
-                prior0 = fmaf(ga, lpth, prior0);
-                prior1 = fmaf(gb, lpth, prior1);
-            }
-            // u = e_j - (G o Theta)_:j
-            u0[i] = (i == j) ? 1.0f : -ga * th;
-            u1[i] = (i == j) ? 1.0f : -gb * th;
-        }
-#ifdef DIBS_QR_FFMA2
-        // experiment (compile with -DDIBS_QR_FFMA2): the two graphs of the slot as one packed pair per row, so each
-        // mat-vec step is ONE FFMA2 with the Rx operand broadcast -- bit-identical results, half the FMA issue slots
-        f32x2 uu[DMAX];
-#pragma unroll
-        for (int i = 0; i < DMAX; ++i) uu[i] = pack2(u0[i], u1[i]);
-        f32x2 ssq2 = 0ull;
-#pragma unroll
-        for (int i = 0; i < DMAX; ++i) {
-            f32x2 a = 0ull;
-#pragma unroll
-            for (int k = i; k < DMAX; ++k) {
-                const float r = R.v[rtri_off<DMAX>(i, k)];
-                a = fma2(pack2(r, r), uu[k], a);
-            }
-            uu[i] = a;
-            ssq2 = fma2(a, a, ssq2);
-        }
-        float ssq0 = lo2(ssq2), ssq1 = hi2(ssq2);
-        if (MODE == MC_THETA_HARD || MODE == MC_Z_REPARAM) {
-#pragma unroll
-            for (int k = DMAX - 1; k >= 0; --k) {
-                f32x2 a = 0ull;
-#pragma unroll
-                for (int i = 0; i <= k; ++i) {
-                    const float r = R.v[rtri_off<DMAX>(i, k)];
-                    a = fma2(pack2(r, r), uu[i], a);
+                for (int w = 0; w < IL; ++w) {
+                    const int i = i0 + w;
+                    float ga = 0.0f, gb = 0.0f;
+                    if (v0 && i < d && i != j) {
+                        ga = p.g_ext[((size_t)m * S + q) * dd + i * d + j];
+                        if (v1) gb = p.g_ext[((size_t)m * S + q + Qh) * dd + i * d + j];
+                    }
+                    x0[w] = __float_as_uint(ga); x1[w] = __float_as_uint(gb);
                 }
-                uu[k] = a;
+            } else {
+#pragma unroll
+                for (int w = 0; w < IL; ++w) { x0[w] = e_row; x1[w] = e_row + half; e_row += (uint32_t)d; }
+                threefry2x32_n<IL>(key.x, key.y, x0, x1);
             }
-        }
 #pragma unroll
-        for (int i = 0; i < DMAX; ++i) { u0[i] = lo2(uu[i]); u1[i] = hi2(uu[i]); }
-#else
-        // y = Rx u (in place, ascending rows), ssq = |y|^2
-        float ssq0 = 0.0f, ssq1 = 0.0f;
-#pragma unroll
-        for (int i = 0; i < DMAX; ++i) {
-            float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-            for (int k = i; k < DMAX; ++k) {
-                const float r = R.v[rtri_off<DMAX>(i, k)];
-                a0 = fmaf(r, u0[k], a0);
-                a1 = fmaf(r, u1[k], a1);
-            }
-            u0[i] = a0; u1[i] = a1;
-            ssq0 = fmaf(a0, a0, ssq0);
-            ssq1 = fmaf(a1, a1, ssq1);
-        }
-        // b = Rx^T y (in place, descending columns) = column j of x^T (x - x (G o Theta))
-        if (MODE == MC_THETA_HARD || MODE == MC_Z_REPARAM) {
-#pragma unroll
-            for (int k = DMAX - 1; k >= 0; --k) {
-                float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-                for (int i = 0; i <= k; ++i) {
-                    const float r = R.v[rtri_off<DMAX>(i, k)];
-                    a0 = fmaf(r, u0[i], a0);
-                    a1 = fmaf(r, u1[i], a1);
+            for (int w = 0; w < IL; ++w) {
+                const int i = i0 + w;
+                // zero_diagonal (utils/func.py:117-125): diagonal draws are consumed and discarded
+                const bool real = v0 && i < d && i != j;
+                float ga = 0.0f, gb = 0.0f;
+                if (real) {
+                    const float sa = sA[i * DMAX + j];
+                    if (use_ext) { ga = __uint_as_float(x0[w]); gb = __uint_as_float(x1[w]); }
+                    else {
+                        ga = entry_from_bits<HARD>(x0[w], sa, fast_soft, p.tau);
+                        gb = v1 ? entry_from_bits<HARD>(x1[w], sa, fast_soft, p.tau) : 0.0f;
+                    }
+                    // log p(theta | G): sum g * logN(theta; mean_edge, sig_edge)   (linearGaussian.py:289)
+                    const float lpth = sLpTh[i * DMAX + j];
+                    prior0 = fmaf(ga, lpth, prior0);
+                    prior1 = fmaf(gb, lpth, prior1);
                 }
-                u0[k] = a0; u1[k] = a1;
+                if (HARD && !use_ext) { gm0 |= (ga != 0.0f ? 1u : 0u) << i; gm1 |= (gb != 0.0f ? 1u : 0u) << i; }
+                else if (active && i < d) { sG[i * DMAX] = ga; sG[MAT + i * DMAX] = gb; }     // own column only
             }
         }
-#endif
-        if (v0) {
-            const float cst = (float)p.n_obs * p.log2pis2;
-            sNode[(2 * slot) * DMAX + j] = prior0 - 0.5f * (cst + ssq0 * inv_s2);
-            sNode[(2 * slot + 1) * DMAX + j] = prior1 - 0.5f * (cst + ssq1 * inv_s2);
-        }
-        __syncthreads();
-        // per-sample log-probs and the round's softmax statistics, by warp 0 (2*gpb <= 32 entries)
-        if (tid < 32) {
-            float lp = -INFINITY;
-            if (tid < 2 * gpb) {
-                const int sl = tid >> 1, wh = tid & 1;
-                const int s = q0 + sl + wh * Qh;
-                if (q0 + sl < q_end && s < S) {
-                    lp = 0.0f;
-                    for (int jj = 0; jj < d; ++jj) lp += sNode[tid * DMAX + jj];
-                    if (p.lp_out) p.lp_out[(size_t)m * S + s] = lp;
+        float* sNd = sNode + buf * (2 * gpb * NS);
+        const float ta = p.tau * alpha;
+        // ---- the two graphs one after the other (same code, half the registers of doing them side by side)
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+            const uint32_t gm = g ? gm1 : gm0;
+            float* sGg = sG + g * MAT;
+            float u[DMAX];                             // u = e_j - (G o Theta)_:j
+#pragma unroll
+            for (int i = 0; i < DMAX; ++i) {
+                float gv = 0.0f, th = 0.0f;
+                if (i < d) {
+                    gv = (HARD && !use_ext) ? (((gm >> i) & 1u) ? 1.0f : 0.0f) : sGg[i * DMAX];
+                    th = sTh[i * DMAX + j];
                 }
-                sLpS[tid] = lp;
+                u[i] = (i == j) ? 1.0f : -gv * th;
             }
+            asm volatile("" ::: "memory");
+            // y = Rx u (in place, ascending rows), ssq = |y|^2; Rx comes from the constant bank
+            float ssq = 0.0f;
+#pragma unroll
+            for (int i = 0; i < DMAX; ++i) {
+                float a = 0.0f;
+#pragma unroll
+                for (int k = i; k < DMAX; ++k) a = fmaf(R.v[rtri_off<DMAX>(i, k)], u[k], a);
+                u[i] = a;
+                ssq = fmaf(a, a, ssq);
+            }
+            // b = Rx^T y (in place, descending columns) = column j of x^T (x - x (G o Theta))
+            if (MODE == MC_THETA_HARD || MODE == MC_Z_REPARAM) {
+#pragma unroll
+                for (int k = DMAX - 1; k >= 0; --k) {
+                    float a = 0.0f;
+#pragma unroll
+                    for (int i = 0; i <= k; ++i) a = fmaf(R.v[rtri_off<DMAX>(i, k)], u[i], a);
+                    u[k] = a;
+                }
+            }
+            if (v0) sNd[(2 * slot + g) * NS + j] = (g ? prior1 : prior0) - 0.5f * (cst + ssq * inv_s2);
+            // compiler fence: the table entries the epilogue needs are RE-LOADED below instead of being carried in
+            // registers across the two mat-vecs (measured: 168 -> ~100 registers)
+            asm volatile("" ::: "memory");
+            // the sample's UNWEIGHTED contribution to the column, parked in the thread's private column until the
+            // softmax weight of the sample is known (after the barrier)
             if (MODE != MC_LP_ONLY) {
-                const float mx = warp_max(lp);
-                const float ex = (lp == -INFINITY) ? 0.0f : expf(lp - fmaxf(mx, m_run));
-                const float se = warp_sum(ex);
-                const float sl_ = warp_sum(lp == -INFINITY ? 0.0f : lp);
-                if (tid == 0) { sStat[0] = mx; sStat[1] = se; sStat[2] = sl_; }
-            }
-        }
-        __syncthreads();
-        if (MODE != MC_LP_ONLY) {
-            const float m_new = fmaxf(m_run, sStat[0]);
-            const float scale = (m_run == -INFINITY) ? 0.0f : expf(m_run - m_new);
-            l_run = l_run * scale + sStat[1];
-            sum_lp += sStat[2];
-            m_run = m_new;
-            const float e0 = v0 ? expf(sLpS[2 * slot] - m_new) : 0.0f;
-            const float e1 = v1 ? expf(sLpS[2 * slot + 1] - m_new) : 0.0f;
-            if (v0) {
 #pragma unroll
                 for (int i = 0; i < DMAX; ++i) {
                     if (i < d) {
-                        const float ga = sG0[i * DMAX], gb = sG1[i * DMAX];
-                        float val0, val1;
+                        float val;
                         if (MODE == MC_THETA_HARD) {
                             // d/dtheta: g * (-(theta-mu)/sig^2) + g * (x^T R)/s2          
                             const float pr = -(sTh[i * DMAX + j] - p.mean_edge) * inv_se2;
-                            val0 = ga * fmaf(u0[i], inv_s2, pr);
-                            val1 = gb * fmaf(u1[i], inv_s2, pr);
+                            const float gv = (HARD && !use_ext) ? (((gm >> i) & 1u) ? 1.0f : 0.0f) : sGg[i * DMAX];
+                            val = gv * fmaf(u[i], inv_s2, pr);
                         } else if (MODE == MC_Z_REPARAM) {
                             // dS = d lp/dG * tau*alpha*g(1-g)                                (App. B-4, B-6)
+                            const float gv = sGg[i * DMAX];
                             const float th = sTh[i * DMAX + j] * inv_s2, lpth = sLpTh[i * DMAX + j];
-                            val0 = fmaf(th, u0[i], lpth) * (p.tau * alpha) * ga * (1.0f - ga);
-                            val1 = fmaf(th, u1[i], lpth) * (p.tau * alpha) * gb * (1.0f - gb);
+                            val = fmaf(th, u[i], lpth) * ta * gv * (1.0f - gv);
                         } else {
-                            val0 = ga; val1 = gb;   // score function: weighted mean graph (App. B-2)
+                            // score function: weighted mean graph (App. B-2)
+                            val = (HARD && !use_ext) ? (((gm >> i) & 1u) ? 1.0f : 0.0f) : sGg[i * DMAX];
                         }
-                        sAcc[i * DMAX] = fmaf(sAcc[i * DMAX], scale, fmaf(e0, val0, e1 * val1));
+                        if (active) sGg[i * DMAX] = val;
                     }
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();                    // the round's only barrier: node log-probs are visible
+        // ---- per-sample log-probs and softmax statistics, by EVERY warp (lane = slot*2 + which; identical results)
+        float lp = -INFINITY;
+        if (lane < 2 * gpb) {
+            const int sl = lane >> 1, wh = lane & 1;
+            const int s = q0 + sl + wh * Qh;
+            if (q0 + sl < q_end && s < S) {
+                lp = 0.0f;
+                for (int jj = 0; jj < d; ++jj) lp += sNd[lane * NS + jj];
+                if (p.lp_out && tid < 32) p.lp_out[(size_t)m * S + s] = lp;
+            }
+        }
+        if (MODE != MC_LP_ONLY) {
+            const float mx = warp_max(lp);
+            const float m_new = fmaxf(m_run, mx);
+            const float ex = (lp == -INFINITY) ? 0.0f : expf(lp - m_new);
+            const float se = warp_sum(ex);
+            const float sl_ = warp_sum(lp == -INFINITY ? 0.0f : lp);
+            const float scale = (m_run == -INFINITY) ? 0.0f : expf(m_run - m_new);
+            l_run = l_run * scale + se;
+            sum_lp += sl_;
+            m_run = m_new;
+            const int src = active ? 2 * slot : 0;
+            const float e0 = __shfl_sync(0xffffffffu, ex, src), e1 = __shfl_sync(0xffffffffu, ex, src + 1);
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < DMAX; ++i)
+                    if (i < d) sAcc[i * DMAX] = fmaf(sAcc[i * DMAX], scale, fmaf(e0, sG[i * DMAX], e1 * sG[MAT + i * DMAX]));
+            }
+        }
+        // no second barrier: the next round writes the OTHER node buffer and only private columns
     }
     if (MODE == MC_LP_ONLY) return;
 
     // deterministic reduction over the slots
+    __syncthreads();
     float* out = p.part_acc + ((size_t)m * p.n_chunks + c) * p.acc_size;
     const float inv_d2 = 1.0f / (float)d;
     for (int e = tid; e < dd; e += blockDim.x) {
         const int i = __float2int_rz(((float)e + 0.5f) * inv_d2), jj = e - i * d;
         float sum = 0.0f;
-        for (int g = 0; g < gpb; ++g) sum += sAccAll[g * MAT + i * DMAX + jj];
+        for (int g = 0; g < gpb; ++g) sum += sAccAll[g * acc_stride + i * DMAX + jj];
         out[e] = sum;
     }
     if (tid == 0) {
@@ -319,8 +288,9 @@ __global__ void __launch_bounds__(192, (DMAX <= 20 ? 2 : 1)) k_mc_lin_qr(const _
 }
 
 inline size_t mc_lin_qr_smem(int dmax, int gpb) {
-    size_t mat = (size_t)dmax * dmax;
-    return (3 * mat + (size_t)gpb * mat + 2 * (size_t)gpb * mat + 2 * (size_t)gpb * dmax + 2 * gpb + 8) * sizeof(float);
+    const size_t mat = (size_t)dmax * dmax;
+    // tables + accumulators + private graph columns (strides padded by at most 31) + node table
+    return (3 * mat + (size_t)gpb * (mat + 31) + (size_t)gpb * (2 * mat + 31) + (size_t)2 * 2 * gpb * (dmax + 1) + 8) * sizeof(float);
 }
 
 }  // namespace dibs

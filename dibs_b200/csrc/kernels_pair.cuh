@@ -6,10 +6,12 @@
 // Closed form: grad_{x_j} k(x_j, x_i) = -(2/h)(x_j - x_i) k_ji, kept in difference form
 // like the reference's autodiff so that near-neighbours do not cancel.
 //
-// Two kernels, each finishing its own reduction: a grid that splits a sum over CTAs (feature splits of the distance
-// pass, j slices of the phi pass) writes the partial planes, counts arrivals per OUTPUT TILE, and the CTA that
-// completes a tile's count sums the planes in FIXED order and applies the epilogue (exp -> K; mean, optimizer step,
-// peer push).  The summation order is the plane index, never the arrival order, and the slicing is a function of
+// Three kernels.  The distance pass splits the feature axis over CTAs and a second, fully parallel kernel sums the
+// split planes and applies exp (both sit on the side branch of the step graph, under the gradient phase -- measured:
+// finishing a tile inside its last-arriving split CTA is 4x slower at 256 particles, 16 busy SMs instead of 148).
+// The phi pass splits the j axis over CTAs, counts arrivals per OUTPUT TILE, and the CTA that completes a tile's count
+// sums the slices in FIXED order and applies the epilogue (mean, optimizer step, peer push): one kernel less on the
+// critical path.  Summation orders are the plane index, never the arrival order, and the slicing is a function of
 // (M, D) only -- results are bit-identical for any number of GPUs and from run to run.
 #pragma once
 #include "common.cuh"
@@ -26,7 +28,6 @@ struct PairParams {
     int n_split, n_split_z;              // feature splits of the distance pass: the first n_split_z cut Z, the rest Theta
     int split_len_z, split_len_t;        // features per split (multiples of 32)
     float* dist_part;                    // [n_split][n_rows][n_all] partial squared distances
-    uint32_t* dist_cnt;                  // [row tiles][column tiles] arrival counters of the distance pass (zero between launches)
     int n_jsplit, j_len;                 // phi: slices of the j axis (j_len on the global index, multiple of 32)
     float* phi_part;                     // [n_jsplit][n_rows][dz+dth] per-slice sums of drive - (2/h) repulsion
     uint32_t* phi_cnt;                   // [row tiles][column tiles] arrival counters of the phi pass
@@ -44,8 +45,7 @@ struct PairParams {
 // ---- pass 1: squared distances -> K.  Tile 64 x 64 outputs, 256 threads x (4 x 4) with INTERLEAVED ownership
 // (rows ty + 16a, columns tx + 16b) so that 128-bit shared-memory reads along the feature axis are conflict-free
 // with a row stride of 36 floats.  blockIdx.z = feature split; a split never straddles the Z | Theta boundary
-// (the first n_split_z splits cut the Z features, the rest the Theta features).  The last split CTA of a tile to
-// arrive sums the split planes in order and applies the SE kernels (kernel.py:30,66-71).
+// (the first n_split_z splits cut the Z features, the rest the Theta features).
 constexpr int KT = 64;    // tile edge
 constexpr int KF = 32;    // features per shared-memory stage
 constexpr int KFP = 36;   // padded row stride (floats): 16-byte aligned, quarter-warp conflict-free
@@ -53,7 +53,6 @@ constexpr int KFP = 36;   // padded row stride (floats): 16-byte aligned, quarte
 __global__ void __launch_bounds__(256) k_pair_dist(PairParams p) {
     __shared__ __align__(16) float sI[KT * KFP];
     __shared__ __align__(16) float sJ[KT * KFP];
-    __shared__ int s_last;
     peer_wait(p.wait_x);
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int j0 = blockIdx.x * KT, i0 = blockIdx.y * KT, sp = blockIdx.z;
@@ -127,56 +126,48 @@ __global__ void __launch_bounds__(256) k_pair_dist(PairParams p) {
             const int gi = i0 + ty + 16 * a, gj = j0 + tx + 16 * b;
             if (gi < p.n_rows && gj < p.n_all) o[(size_t)gi * p.n_all + gj] = lo2(acc[a][b]) + hi2(acc[a][b]);
         }
-    // ---- the tile's last split CTA turns the summed distances into K_z, K_theta and K = K_z + K_theta
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t* cnt = p.dist_cnt + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-        const unsigned old = atomicAdd(cnt, 1u);
-        s_last = (old == (unsigned)p.n_split - 1u) ? 1 : 0;
-        if (s_last) *cnt = 0u;                     // re-armed for the next launch
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+}
+
+// ---- pass 1b: sum the feature splits in fixed order, apply the SE kernels (kernel.py:30,66-71)
+__global__ void __launch_bounds__(256) k_pair_finish(PairParams p) {
+    const size_t plane = (size_t)p.n_rows * p.n_all;
     const int nz = p.n_split_z, nt = p.n_split - p.n_split_z;
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int gi = i0 + ty + 16 * a, gj = j0 + tx + 16 * b;
-            if (gi >= p.n_rows || gj >= p.n_all) continue;
-            const size_t e = (size_t)gi * p.n_all + gj;
-            float dz = 0.0f, dt = 0.0f;
-            for (int s = 0; s < nz; ++s) dz += __ldcg(p.dist_part + (size_t)s * plane + e);
-            for (int s = 0; s < nt; ++s) dt += __ldcg(p.dist_part + (size_t)(nz + s) * plane + e);
-            const float kz = p.scale_z * expf(-dz / p.h_z);
-            const float kt = p.dth > 0 ? p.scale_t * expf(-dt / p.h_t) : 0.0f;
-            p.kz[e] = kz;
-            if (p.kt) p.kt[e] = kt;
-            p.kfull[e] = kz + kt;
-        }
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < plane; e += (size_t)gridDim.x * blockDim.x) {
+        float dz = 0.0f, dt = 0.0f;
+#pragma unroll 4
+        for (int s = 0; s < nz; ++s) dz += p.dist_part[(size_t)s * plane + e];
+#pragma unroll 4
+        for (int s = 0; s < nt; ++s) dt += p.dist_part[(size_t)(nz + s) * plane + e];
+        float kz = p.scale_z * expf(-dz / p.h_z);
+        float kt = p.dth > 0 ? p.scale_t * expf(-dt / p.h_t) : 0.0f;
+        p.kz[e] = kz;
+        if (p.kt) p.kt[e] = kt;
+        p.kfull[e] = kz + kt;
+    }
 }
 
 // ---- pass 2: phi_i = -(1/M) sum_j [ K_ij g_j - (2/h) Kterm_ij (x_j - x_i) ], then the optimizer step.
-// Tile: 64 rows x 64 feature columns per CTA, 128 threads x (8 rows x 4 columns).  Per particle j a thread issues
-// six 128-bit shared-memory loads (K and Kterm for its 8 rows, x_j and g_j for its 4 columns) for 48 packed FP
-// instructions; the row weight enters the FFMA2 as a broadcast scalar.
+// Tile: (8 RPT) rows x 64 feature columns per CTA, 128 threads x (RPT rows x 4 columns).  RPT = 8 (64-row tiles): per
+// particle j a thread issues six 128-bit shared-memory loads (K and Kterm for its 8 rows, x_j and g_j for its 4
+// columns) for 48 packed FP instructions -- 12 % faster than RPT = 4 at 1024 rows per rank; RPT = 4 (32-row tiles)
+// where a rank owns few rows, so that twice as many CTAs share the epilogue.  The row weight enters the FFMA2 as a
+// broadcast scalar.  Every output element is the same fixed-order sum whatever the tile height.
 // blockIdx.z = slice of the j axis (fixed length j_len on the GLOBAL particle index).  The last slice CTA of a tile to
 // arrive sums the slices in order -> phi, applies RMSprop / SGD to its 64 x 64 block of the rank's rows and -- on
 // several GPUs -- stores the updated block into every peer's next particle buffer (fused exchange).
 constexpr int PT_C = 64, PT_J = 32;
-constexpr int PB_I = 64;
-constexpr int PB_KP = 68;   // padded stride of the transposed K tiles [j][i]
 
+template <int RPT>
 __global__ void __launch_bounds__(128) k_phi(PairParams p) {
+    constexpr int PB_I = 8 * RPT;       // rows per tile
+    constexpr int PB_KP = PB_I + 4;     // padded stride of the transposed K tiles [j][i]
     __shared__ __align__(16) float sK[PT_J * PB_KP];      // K_full[i][j] transposed: [j][i]
     __shared__ __align__(16) float sKt[PT_J * PB_KP];     // K term (z or theta block)
     __shared__ __align__(16) float sXj[PT_J * PT_C];
     __shared__ __align__(16) float sGj[PT_J * PT_C];
     __shared__ int s_last;
     peer_wait(p.wait_g);
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;      // ty 0..7: rows 8 ty .. 8 ty + 7
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;      // ty 0..7: rows RPT ty .. RPT ty + RPT - 1
     const int i0 = blockIdx.y * PB_I;
     const int D = p.dz + p.dth;
     // a column tile never straddles the Z | Theta boundary: grid.x = ceil(dz/64) + ceil(dth/64)
@@ -189,12 +180,12 @@ __global__ void __launch_bounds__(128) k_phi(PairParams p) {
     const int j_begin = blockIdx.z * p.j_len;
     const int j_end = min(p.n_all, j_begin + p.j_len);
 
-    f32x2 xi[8][2], drive[8][2], rep[8][2];               // [row][column pair]
+    f32x2 xi[RPT][2], drive[RPT][2], rep[RPT][2];         // [row][column pair]
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+    for (int a = 0; a < RPT; ++a)
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
-            const int gi = i0 + ty * 8 + a, gc = c0 + tx * 4 + 2 * b;
+            const int gi = i0 + ty * RPT + a, gc = c0 + tx * 4 + 2 * b;
             const float* xr = p.x_all + (size_t)(p.row0 + gi) * p.ld;
             const float v0 = (gi < p.n_rows && gc < c_end) ? xr[gc] : 0.0f;
             const float v1 = (gi < p.n_rows && gc + 1 < c_end) ? xr[gc + 1] : 0.0f;
@@ -235,16 +226,18 @@ __global__ void __launch_bounds__(128) k_phi(PairParams p) {
         const int nj = min(PT_J, j_end - j0);
 #pragma unroll 2
         for (int j = 0; j < nj; ++j) {
-            const float4 kfa = *reinterpret_cast<const float4*>(&sK[j * PB_KP + ty * 8]);
-            const float4 kfb = *reinterpret_cast<const float4*>(&sK[j * PB_KP + ty * 8 + 4]);
-            const float4 kta = *reinterpret_cast<const float4*>(&sKt[j * PB_KP + ty * 8]);
-            const float4 ktb = *reinterpret_cast<const float4*>(&sKt[j * PB_KP + ty * 8 + 4]);
+            float kf[RPT], kt[RPT];
+#pragma unroll
+            for (int q = 0; q < RPT / 4; ++q) {
+                const float4 kfa = *reinterpret_cast<const float4*>(&sK[j * PB_KP + ty * RPT + 4 * q]);
+                const float4 kta = *reinterpret_cast<const float4*>(&sKt[j * PB_KP + ty * RPT + 4 * q]);
+                kf[4 * q] = kfa.x; kf[4 * q + 1] = kfa.y; kf[4 * q + 2] = kfa.z; kf[4 * q + 3] = kfa.w;
+                kt[4 * q] = kta.x; kt[4 * q + 1] = kta.y; kt[4 * q + 2] = kta.z; kt[4 * q + 3] = kta.w;
+            }
             const ulonglong2 xj = *reinterpret_cast<const ulonglong2*>(&sXj[j * PT_C + tx * 4]);
             const ulonglong2 gj = *reinterpret_cast<const ulonglong2*>(&sGj[j * PT_C + tx * 4]);
-            const float kf[8] = {kfa.x, kfa.y, kfa.z, kfa.w, kfb.x, kfb.y, kfb.z, kfb.w};
-            const float kt[8] = {kta.x, kta.y, kta.z, kta.w, ktb.x, ktb.y, ktb.z, ktb.w};
 #pragma unroll
-            for (int a = 0; a < 8; ++a) {
+            for (int a = 0; a < RPT; ++a) {
                 const f32x2 kfa2 = pack2(kf[a], kf[a]), kta2 = pack2(kt[a], kt[a]);
                 drive[a][0] = fma2(kfa2, gj.x, drive[a][0]);
                 drive[a][1] = fma2(kfa2, gj.y, drive[a][1]);
@@ -260,8 +253,8 @@ __global__ void __launch_bounds__(128) k_phi(PairParams p) {
     float* part = p.phi_part + (size_t)blockIdx.z * plane;
     const int gc = c0 + tx * 4;
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
-        const int gi = i0 + ty * 8 + a;
+    for (int a = 0; a < RPT; ++a) {
+        const int gi = i0 + ty * RPT + a;
         if (gi >= p.n_rows) continue;
         float* o = part + (size_t)gi * D + gc;
         const float v0 = fmaf(c2, lo2(rep[a][0]), lo2(drive[a][0])), v1 = fmaf(c2, hi2(rep[a][0]), hi2(drive[a][0]));
@@ -288,38 +281,81 @@ __global__ void __launch_bounds__(128) k_phi(PairParams p) {
     if (!s_last) return;
     __threadfence();
     const float inv_m = 1.0f / (float)p.n_all;
+    // a thread's 4 columns move as one 128-bit access wherever the row layout allows (always, for the plan's own
+    // buffers when dz is a multiple of 4): the peer stores of a warp then cover two rows x 256 contiguous bytes
+    const bool full = gc + 3 < c_end;
 #pragma unroll 2
-    for (int a = 0; a < 8; ++a) {
-        const int gi = i0 + ty * 8 + a;
-        if (gi < p.n_rows) {
-            float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            const float* pr = p.phi_part + (size_t)gi * D + gc;
+    for (int a = 0; a < RPT; ++a) {
+        const int gi = i0 + ty * RPT + a;
+        if (gi >= p.n_rows) continue;
+        float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        const float* pr = p.phi_part + (size_t)gi * D + gc;
+        if (full && ((plane | ((size_t)gi * D + gc)) & 3) == 0) {
+#pragma unroll 8
+            for (int s = 0; s < p.n_jsplit; ++s) {
+                const float4 v4 = __ldcg(reinterpret_cast<const float4*>(pr + (size_t)s * plane));
+                sum[0] += v4.x; sum[1] += v4.y; sum[2] += v4.z; sum[3] += v4.w;
+            }
+        } else {
             for (int s = 0; s < p.n_jsplit; ++s) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     if (gc + u < c_end) sum[u] += __ldcg(pr + (size_t)s * plane + u);
             }
-            const float xc[4] = {lo2(xi[a][0]), hi2(xi[a][0]), lo2(xi[a][1]), hi2(xi[a][1])};
+        }
+        const float xc[4] = {lo2(xi[a][0]), hi2(xi[a][0]), lo2(xi[a][1]), hi2(xi[a][1])};
+        float phi[4], xn[4], vn[4];
+        float* vp = p.v ? p.v + (size_t)gi * p.v_ld + gc : nullptr;
+        const bool vec_v = full && p.x_next && p.optimizer == 1 && ((((size_t)gi * p.v_ld + gc) & 3) == 0);
+        float vo[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (p.x_next && p.optimizer == 1) {
+            if (vec_v) { const float4 v4 = *reinterpret_cast<const float4*>(vp); vo[0] = v4.x; vo[1] = v4.y; vo[2] = v4.z; vo[3] = v4.w; }
+            else {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = gc + u;
-                if (e >= c_end) continue;
-                // -(weighted_gradient_ascent + repulsion).mean(axis=0)   (svgd.py:212-216)
-                const float phi = -sum[u] * inv_m;
-                if (p.phi_out) p.phi_out[(size_t)gi * p.phi_ld + e] = phi;
-                if (p.x_next) {
-                    float x = xc[u];
-                    if (p.optimizer == 1) {
-                        // rmsprop(step, gamma=0.9, eps=1e-8): v = v*gamma + g^2*(1-gamma); x -= step*g/sqrt(v+eps)
-                        float* vp = p.v + (size_t)gi * p.v_ld + e;
-                        const float v = __fadd_rn(__fmul_rn(*vp, 0.9f), __fmul_rn(__fmul_rn(phi, phi), 0.1f));
-                        *vp = v;
-                        x = __fsub_rn(x, __fdiv_rn(__fmul_rn(p.stepsize, phi), __fsqrt_rn(__fadd_rn(v, 1e-8f))));
-                    } else {
-                        x = __fsub_rn(x, __fmul_rn(p.stepsize, phi));   // sgd: x - step * g
-                    }
-                    p.x_next[(size_t)gi * p.next_ld + e] = x;
-                    if (p.push_x.world) peer_store(p.push_x, (size_t)(p.row0 + gi) * p.next_ld + e, x);
+                for (int u = 0; u < 4; ++u) if (gc + u < c_end) vo[u] = vp[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            // -(weighted_gradient_ascent + repulsion).mean(axis=0)   (svgd.py:212-216)
+            phi[u] = -sum[u] * inv_m;
+            if (p.optimizer == 1) {
+                // rmsprop(step, gamma=0.9, eps=1e-8): v = v*gamma + g^2*(1-gamma); x -= step*g/sqrt(v+eps)
+                vn[u] = __fadd_rn(__fmul_rn(vo[u], 0.9f), __fmul_rn(__fmul_rn(phi[u], phi[u]), 0.1f));
+                xn[u] = __fsub_rn(xc[u], __fdiv_rn(__fmul_rn(p.stepsize, phi[u]), __fsqrt_rn(__fadd_rn(vn[u], 1e-8f))));
+            } else {
+                vn[u] = 0.0f;
+                xn[u] = __fsub_rn(xc[u], __fmul_rn(p.stepsize, phi[u]));   // sgd: x - step * g
+            }
+        }
+        if (p.phi_out) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (gc + u < c_end) p.phi_out[(size_t)gi * p.phi_ld + gc + u] = phi[u];
+        }
+        if (p.x_next) {
+            if (p.optimizer == 1) {
+                if (vec_v) *reinterpret_cast<float4*>(vp) = make_float4(vn[0], vn[1], vn[2], vn[3]);
+                else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (gc + u < c_end) vp[u] = vn[u];
+                }
+            }
+            const size_t off_loc = (size_t)gi * p.next_ld + gc;                    // in this rank's rows
+            const size_t off_all = (size_t)(p.row0 + gi) * p.next_ld + gc;         // in a whole particle buffer
+            if (full && (((uintptr_t)(p.x_next + off_loc)) & 15) == 0) {
+                const float4 x4 = make_float4(xn[0], xn[1], xn[2], xn[3]);
+                *reinterpret_cast<float4*>(p.x_next + off_loc) = x4;
+                if (p.push_x.world) {
+#pragma unroll 1
+                    for (int q = 0; q < p.push_x.world; ++q)
+                        if (q != p.push_x.rank) *reinterpret_cast<float4*>(p.push_x.dst[q] + off_all) = x4;
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (gc + u >= c_end) continue;
+                    p.x_next[off_loc + u] = xn[u];
+                    if (p.push_x.world) peer_store(p.push_x, off_all + u, xn[u]);
                 }
             }
         }

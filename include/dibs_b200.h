@@ -139,8 +139,8 @@ enum {
                                    serial per-kernel mode this phase carries it */
     DIBS_PHASE_ASSEMBLE = 3,    /* (hooks only) stand-alone assemble kernel                  */
     DIBS_PHASE_ALLGATHER = 4,   /* NCCL all-gather (multi-GPU fallback path only)            */
-    DIBS_PHASE_PAIR_DIST = 5,   /* pairwise squared distances -> K (kernel.py:30,66-71)      */
-    DIBS_PHASE_PAIR_KERNEL = 6, /* (unused: exp -> K is the epilogue of the distance kernel) */
+    DIBS_PHASE_PAIR_DIST = 5,   /* pairwise squared distances (kernel.py:30,66-71)           */
+    DIBS_PHASE_PAIR_KERNEL = 6, /* sum of the feature splits, exp -> K (kernel.py:30,66-71)  */
     DIBS_PHASE_PHI_UPDATE = 7,  /* phi + optimizer step + peer push (svgd.py:194-224,591-670,265,718-719) */
     DIBS_PHASE_STEP_KEYS = 8,   /* next step's raw scores U V^T = the edge-probability pass (dibs.py:179-181) */
     DIBS_N_PHASES = 9

@@ -129,8 +129,8 @@ def test_bench_work_model_covers_every_phase():
             work = bench.kernel_work(name, m // world, m)
             joint = lik != "bge"
             for ph in nat.PHASES:
-                if (ph == "mc_theta" and not joint) or ph in ("assemble", "pair_kernel"):
-                    continue                     # hook-only phases: fused into "acyclic" / "pair_dist" in the step
+                if (ph == "mc_theta" and not joint) or ph == "assemble":
+                    continue                     # hook-only phase: fused into the gradient kernels in the step
                 assert ph in work, (name, ph)
                 assert work[ph]["bytes"] >= 0 and work[ph]["flops"] >= 0
             fp32_tf, fp64_tf, _ = bench.simt_peaks()

@@ -12,7 +12,7 @@ import statistics
 import subprocess
 import sys
 
-PHASE_OF = [("k_mc_", None), ("k_acyclic", "acyclic"), ("k_pair_dist", "pair_dist"), ("k_phi", "phi_update"),
+PHASE_OF = [("k_mc_", None), ("k_acyclic", "acyclic"), ("k_pair_dist", "pair_dist"), ("k_pair_finish", "pair_kernel"), ("k_phi", "phi_update"),
             ("k_prologue", "scores")]
 
 
