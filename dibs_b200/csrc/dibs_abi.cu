@@ -816,7 +816,14 @@ static int stream_edge(cudaStream_t from, cudaStream_t to, cudaEvent_t ev) {
 
 static int ensure_aux(dibs_plan* p) {
     for (int i = 0; i < 3; ++i) {
-        if (!p->aux[i]) CU(cudaStreamCreateWithFlags(&p->aux[i], cudaStreamNonBlocking));
+        if (!p->aux[i]) {
+            // EXPERIMENT knob DIBS_X_PRIO: sibling branches at high priority, so that the MAIN branch's kernel finishes
+            // last and the join in front of phi is not a cross-branch edge on the critical path
+            static const int x_prio = getenv("DIBS_X_PRIO") ? atoi(getenv("DIBS_X_PRIO")) : 0;
+            int least = 0, greatest = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            CU(cudaStreamCreateWithPriority(&p->aux[i], cudaStreamNonBlocking, x_prio ? greatest : least));
+        }
         if (!p->ev_join[i]) CU(cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < 2; ++i) if (!p->ev_fork[i]) CU(cudaEventCreateWithFlags(&p->ev_fork[i], cudaEventDisableTiming));
@@ -848,11 +855,12 @@ static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_st
     fuse.total = (joint ? sh.chunks : 0) + sh.chunks + a.acyc_chunks;
 
     McParams q;
-    cudaStream_t s_th = conc ? p->aux[0] : stream, s_ac = conc ? p->aux[1] : stream;
+    static const int x_acyc_inline = getenv("DIBS_X_ACYC_INLINE") ? atoi(getenv("DIBS_X_ACYC_INLINE")) : 0;   // EXPERIMENT
+    cudaStream_t s_th = conc ? p->aux[0] : stream, s_ac = (conc && !x_acyc_inline) ? p->aux[1] : stream;
     if (conc) {
         CU(cudaEventRecord(p->ev_fork[1], stream));
         if (joint) CU(cudaStreamWaitEvent(s_th, p->ev_fork[1], 0));
-        CU(cudaStreamWaitEvent(s_ac, p->ev_fork[1], 0));
+        if (s_ac != stream) CU(cudaStreamWaitEvent(s_ac, p->ev_fork[1], 0));
     }
     if (joint) {
         fill_mc(p, s, q);
@@ -873,7 +881,7 @@ static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_st
     mark(p, s_ac, DIBS_PHASE_ACYCLIC);
     if (conc) {
         if (joint) TRY(stream_edge(s_th, stream, p->ev_join[0]));
-        TRY(stream_edge(s_ac, stream, p->ev_join[1]));
+        if (s_ac != stream) TRY(stream_edge(s_ac, stream, p->ev_join[1]));
     }
     return DIBS_OK;
 }
@@ -964,8 +972,9 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream, bool conc) {
     // the kernel matrix needs the particles only: it runs on a side branch under the gradient phase.  On several GPUs
     // the rows every rank updated at the end of the previous step were stored into this rank's buffer by the peers'
     // phi kernels (the distance kernel waits on their flags) or, on the NCCL path, arrive by an all-gather here
-    cudaStream_t s_k = conc ? p->aux[2] : stream;
-    if (conc) TRY(stream_edge(stream, s_k, p->ev_fork[0]));
+    static const int x_pair_inline = getenv("DIBS_X_PAIR_INLINE") ? atoi(getenv("DIBS_X_PAIR_INLINE")) : 0;   // EXPERIMENT
+    cudaStream_t s_k = (conc && !x_pair_inline) ? p->aux[2] : stream;
+    if (conc && s_k != stream) TRY(stream_edge(stream, s_k, p->ev_fork[0]));
     if (multi && !p->p2p) {
         NC(g_nccl.AllGather(loc, P, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm_x, s_k));
         mark(p, s_k, DIBS_PHASE_ALLGATHER);
@@ -984,7 +993,7 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream, bool conc) {
         NC(g_nccl.AllGather(gloc, G, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm, stream));
         mark(p, stream, DIBS_PHASE_ALLGATHER);
     }
-    if (conc) TRY(stream_edge(s_k, stream, p->ev_join[2]));
+    if (conc && s_k != stream) TRY(stream_edge(s_k, stream, p->ev_join[2]));
     q.x_next = Pn + (size_t)p->row0 * p->ld; q.next_ld = p->ld;
     q.v = p->v; q.v_ld = p->D;
     if (fuse) fill_push(p, q.push_x, PEER_KIND_X, p->peer_pk[cur ^ 1]);
@@ -1309,22 +1318,26 @@ struct Scratch {
     }
 };
 
-extern "C" int dibs_edge_probs(dibs_plan* p, const float* z, int32_t n, int32_t t, float* p_out, void* stream_) {
-    if (!p || !z || !p_out || n < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_edge_probs: bad arguments");
-    size_t smem = (size_t)2 * p->d * p->k * sizeof(float);
+static int launch_edge_probs(dibs_plan* p, const float* z, int n, float alpha, float* p_out, int32_t* g_out, cudaStream_t stream) {
+    const int warps = edge_probs_warps(p->d, p->k);
+    const size_t smem = warps * edge_probs_smem_per_warp(p->d, p->k);
     TRY(set_smem(k_edge_probs, smem));
-    k_edge_probs<<<n, 256, smem, (cudaStream_t)stream_>>>(z, p->Dz, p->d, p->k, p->cfg.alpha_linear * (float)t, p_out, nullptr);
+    int blocks = ceil_div(n, warps);
+    const int cap = 148 * 6;                      // grid-stride beyond ~6 CTAs per SM
+    if (blocks > cap) blocks = cap;
+    k_edge_probs<<<blocks, warps * 32, smem, stream>>>(z, p->Dz, n, p->d, p->k, alpha, p_out, g_out);
     LAUNCHED();
     return DIBS_OK;
 }
 
+extern "C" int dibs_edge_probs(dibs_plan* p, const float* z, int32_t n, int32_t t, float* p_out, void* stream_) {
+    if (!p || !z || !p_out || n < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_edge_probs: bad arguments");
+    return launch_edge_probs(p, z, n, p->cfg.alpha_linear * (float)t, p_out, nullptr, (cudaStream_t)stream_);
+}
+
 extern "C" int dibs_particle_to_g_lim(dibs_plan* p, const float* z, int32_t n, int32_t* g_out, void* stream_) {
     if (!p || !z || !g_out || n < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_particle_to_g_lim: bad arguments");
-    size_t smem = (size_t)2 * p->d * p->k * sizeof(float);
-    TRY(set_smem(k_edge_probs, smem));
-    k_edge_probs<<<n, 256, smem, (cudaStream_t)stream_>>>(z, p->Dz, p->d, p->k, 0.0f, nullptr, g_out);
-    LAUNCHED();
-    return DIBS_OK;
+    return launch_edge_probs(p, z, n, 0.0f, nullptr, g_out, (cudaStream_t)stream_);
 }
 
 extern "C" int dibs_sample_graphs(dibs_plan* p, const float* probs, const uint32_t* keys, int32_t n, int32_t n_samples,

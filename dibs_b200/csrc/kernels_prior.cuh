@@ -280,19 +280,100 @@ __global__ void __launch_bounds__(256) k_assemble_grad(const __grid_constant__ A
     assemble_particle(p, blockIdx.x, smem);
 }
 
-// edge_probs / particle_to_g_lim hooks (dibs.py:84-99,168-184); one CTA per particle
-__global__ void __launch_bounds__(256) k_edge_probs(const float* z, int z_ld, int d, int k, float alpha,
-                                                    float* p_out, int32_t* g_lim_out) {
+// edge_probs / particle_to_g_lim (dibs.py:84-99,168-184): the edge-probability pass as a stand-alone, HBM-bound
+// kernel (algorithmic traffic: read Z once, 8dk bytes, write P once, 4d^2 bytes per particle; AI = d/6 flop/B).
+// One WARP per particle, 8 particles in flight per CTA, grid-stride over particles:
+//   * the latent row arrives as coalesced 128-bit loads and is de-interleaved into sU[kk][i], sV[kk][j] (leading
+//     dimension LD = d rounded up to 4, so a thread's 4 consecutive i / j are one 128-bit shared-memory read);
+//   * lane (ti, tj) owns a 4 x 4 tile of U V^T: two LDS.128 per 16 FMAs -- without the register tile the kernel
+//     is bound by shared-memory bandwidth (2 loads per FMA) at ~12 % of the HBM roofline (measured, round 2);
+//   * the d x d result is staged in shared memory and leaves as coalesced 128-bit stores.
+constexpr int EP_WARPS = 8;     // particles in flight per CTA (fewer when a particle's tiles need more shared memory)
+
+inline size_t edge_probs_smem_per_warp(int d, int k) {
+    const int ld = (d + 3) & ~3;
+    return ((size_t)2 * k * ld + (size_t)ld * ld + 4) * sizeof(float);
+}
+inline int edge_probs_warps(int d, int k) {
+    int w = (int)((200 * 1024) / edge_probs_smem_per_warp(d, k));
+    return w < 1 ? 1 : (w > EP_WARPS ? EP_WARPS : w);
+}
+
+__global__ void __launch_bounds__(EP_WARPS * 32) k_edge_probs(const float* __restrict__ z, int z_ld, int n, int d, int k,
+                                                             float alpha, float* __restrict__ p_out,
+                                                             int32_t* __restrict__ g_lim_out) {
     extern __shared__ __align__(16) float smem[];
-    const float* zrow = z + (size_t)blockIdx.x * z_ld;
-    for (int e = threadIdx.x; e < 2 * d * k; e += blockDim.x) smem[e] = zrow[e];
-    __syncthreads();
-    for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
-        int i = e / d, j = e % d;
-        float acc = 0.0f;
-        for (int kk = 0; kk < k; ++kk) acc = fmaf(smem[(i * k + kk) * 2], smem[(j * k + kk) * 2 + 1], acc);
-        if (p_out) p_out[(size_t)blockIdx.x * d * d + e] = (i == j) ? 0.0f : sigmoidf_ref(alpha * acc);
-        if (g_lim_out) g_lim_out[(size_t)blockIdx.x * d * d + e] = (i != j && acc > 0.0f) ? 1 : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ld = (d + 3) & ~3, tq = ld >> 2;                 // tq x tq register tiles of 4 x 4
+    const int per_warp = 2 * k * ld + ld * ld + 4;
+    float* sU = smem + (size_t)warp * per_warp;                // [k][ld]
+    float* sV = sU + k * ld;                                   // [k][ld]
+    float* sP = sV + k * ld;                                   // [d][ld] staged result
+    const int dk2 = 2 * d * k, dd = d * d;
+    const bool vec_in = ((z_ld & 3) == 0) && ((dk2 & 3) == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
+    const int n_warps = blockDim.x >> 5;
+    for (int m = blockIdx.x * n_warps + warp; m < n; m += gridDim.x * n_warps) {
+        const float* zrow = z + (size_t)m * z_ld;
+        // zero the padding columns once per particle (cheap; keeps the tiles branch-free)
+        for (int e = lane; e < 2 * k * (ld - d); e += 32) {
+            const int kk = e / (ld - d), c = d + e % (ld - d);
+            (kk < k ? sU : sV)[(kk % k) * ld + c] = 0.0f;
+        }
+        if (vec_in) {
+            for (int e4 = lane; e4 < dk2 / 4; e4 += 32) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(zrow) + e4);
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = 4 * e4 + u, i = e / (2 * k), r = e - i * 2 * k;
+                    ((r & 1) ? sV : sU)[(r >> 1) * ld + i] = vv[u];
+                }
+            }
+        } else {
+            for (int e = lane; e < dk2; e += 32) {
+                const int i = e / (2 * k), r = e - i * 2 * k;
+                ((r & 1) ? sV : sU)[(r >> 1) * ld + i] = zrow[e];
+            }
+        }
+        __syncwarp();
+        for (int tile = lane; tile < tq * tq; tile += 32) {
+            const int ti = tile / tq, tj = tile - ti * tq;
+            float acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+            const float* up = sU + 4 * ti;
+            const float* vp = sV + 4 * tj;
+            for (int kk = 0; kk < k; ++kk, up += ld, vp += ld) {
+                const float4 u4 = *reinterpret_cast<const float4*>(up);
+                const float4 v4 = *reinterpret_cast<const float4*>(vp);
+                const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(uu[a], vv[b], acc[a][b]);     // same kk order as every other U V^T
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int i = 4 * ti + a, j = 4 * tj + b;
+                    float v;
+                    if (p_out) v = (i == j) ? 0.0f : sigmoidf_ref(alpha * acc[a][b]);
+                    else v = __int_as_float((i != j && acc[a][b] > 0.0f) ? 1 : 0);
+                    if (i < d && j < d) sP[i * d + j] = v;                                      // packed [d][d]
+                }
+        }
+        __syncwarp();
+        float* out = p_out ? p_out + (size_t)m * dd : reinterpret_cast<float*>(g_lim_out + (size_t)m * dd);
+        if (((dd & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+            for (int e4 = lane; e4 < dd / 4; e4 += 32)
+                __stcs(reinterpret_cast<float4*>(out) + e4, *reinterpret_cast<const float4*>(sP + 4 * e4));
+        } else {
+            for (int e = lane; e < dd; e += 32) out[e] = sP[e];
+        }
+        __syncwarp();
     }
 }
 
