@@ -22,6 +22,7 @@
 #include "kernels_acyclic.cuh"
 #include "kernels_dense.cuh"
 #include "kernels_pair.cuh"
+#include "kernels_phi_mma.cuh"
 #include "kernels_init.cuh"
 
 using namespace dibs;
@@ -156,6 +157,10 @@ struct dibs_plan {
     // arrival counters of the in-kernel reductions (zero between launches): gradient CTAs per particle (fused
     // assemble), feature splits per K tile, j slices per phi tile
     uint32_t *arrive = nullptr, *phi_cnt = nullptr;
+    // tensor-core phi (kernels_phi_mma.cuh): TMA tensor maps of the K planes and, per buffer parity, of the particle
+    // and gradient buffers; chosen by the GLOBAL particle count only, so every world size takes the same arithmetic
+    bool phi_mma = false;
+    PhiMmaMaps mma_maps[2];
     // CUDA graphs of one step, per buffer parity
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
     int kernels_per_step = 0;
@@ -421,6 +426,47 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
     return DIBS_OK;
 }
 
+// ---- TMA tensor maps (driver entry point resolved at run time: the library does not link libcuda) -----------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (EncodeTiledFn)sym;
+    }();
+    return fn;
+}
+// fp32 row-major matrix [rows][cols] with row stride `ld` floats; box = 32 columns (one 128-byte swizzle row) x box_rows
+static int make_map(CUtensorMap* m, const float* base, size_t rows, size_t cols, size_t ld, unsigned box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(DIBS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {32u, box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DIBS_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return DIBS_OK;
+}
+static bool phi_mma_eligible(int n_all, int ld) {
+    static const bool off = getenv("DIBS_B200_PHI_SIMT") && getenv("DIBS_B200_PHI_SIMT")[0] == '1';      // debugging: SIMT phi everywhere
+    return !off && n_all >= 128 && (n_all % 4) == 0 && (ld % 4) == 0;
+}
+static int fill_mma_maps(PhiMmaMaps& mm, const float* kfull, const float* kz, const float* kt, int n_rows, int n_all,
+                         const float* x_all, const float* g_all, int ld) {
+    TRY(make_map(&mm.a_full, kfull, n_rows, n_all, n_all, MM_ROWS));
+    TRY(make_map(&mm.a_z, kz, n_rows, n_all, n_all, MM_ROWS));
+    TRY(make_map(&mm.a_t, kt ? kt : kz, n_rows, n_all, n_all, MM_ROWS));
+    TRY(make_map(&mm.b_x, x_all, n_all, ld, ld, MM_KS));
+    TRY(make_map(&mm.b_g, g_all, n_all, ld, ld, MM_KS));
+    return DIBS_OK;
+}
+
 // Workspace of the step loop (particle / gradient buffers, Monte-Carlo partials, pairwise planes): allocated by the
 // first dibs_svgd_steps / dibs_plan_ipc_export call, so plans that only serve the per-function hooks stay a few KB.
 static int ensure_step_ws(dibs_plan* p) {
@@ -464,6 +510,10 @@ static int ensure_step_ws(dibs_plan* p) {
         (r = alloc((void**)&p->kt, plane)) || (r = alloc((void**)&p->kfull, plane)) ||
         (r = alloc((void**)&p->phi_part, (size_t)p->n_jsplit * p->M_loc * p->D * sizeof(float))))
         return r;
+    p->phi_mma = phi_mma_eligible(p->M, p->ld);
+    if (p->phi_mma)
+        for (int par = 0; par < 2; ++par)
+            TRY(fill_mma_maps(p->mma_maps[par], p->kfull, p->kz, p->Dth ? p->kt : nullptr, p->M_loc, p->M, p->pk[par], p->gk[par], p->ld));
     p->step_ws = true;
     return DIBS_OK;
 }
@@ -912,7 +962,17 @@ static int launch_kmat(dibs_plan* p, const PairParams& q, cudaStream_t stream) {
 }
 
 // phi partial sums per j slice, finished (mean, optimizer step, peer push) by each tile's last slice CTA
-static int launch_phi(dibs_plan* p, const PairParams& q, cudaStream_t stream) {
+static int launch_phi(dibs_plan* p, const PairParams& q, cudaStream_t stream, const PhiMmaMaps* mma = nullptr) {
+    if (mma) {
+        // tensor-core path: 128-row x 64-column tiles per j slice, operands by TMA, 3 x TF32 into TMEM
+        static bool attr_set = false;
+        if (!attr_set) { CU(cudaFuncSetAttribute(k_phi_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES)); attr_set = true; }
+        dim3 gm(ceil_div(q.dz, MM_COLS) + ceil_div(q.dth, MM_COLS), ceil_div(q.n_rows, MM_ROWS), q.n_jsplit);
+        k_phi_mma<<<gm, MM_THREADS, MM_SMEM_BYTES, stream>>>(q, *mma);
+        LAUNCHED();
+        mark(p, stream, DIBS_PHASE_PHI_UPDATE);
+        return DIBS_OK;
+    }
     // 64-row tiles once a rank owns enough rows to fill the GPU with them, 32-row tiles below (twice the CTAs)
     const int cols = ceil_div(q.dz, PT_C) + ceil_div(q.dth, PT_C);
     if (q.n_rows >= 512) k_phi<8><<<dim3(cols, ceil_div(q.n_rows, 64), q.n_jsplit), 128, 0, stream>>>(q);
@@ -998,7 +1058,7 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream, bool conc) {
     q.v = p->v; q.v_ld = p->D;
     if (fuse) fill_push(p, q.push_x, PEER_KIND_X, p->peer_pk[cur ^ 1]);
     if (p->tl_capture >= 0) mark(p, stream, DIBS_PHASE_ASSEMBLE);     // timeline diagnostics: the join point before phi
-    TRY(launch_phi(p, q, stream));
+    TRY(launch_phi(p, q, stream, p->phi_mma ? &p->mma_maps[cur] : nullptr));
     // raw scores U V^T of the NEXT step from the updated latent rows (edge-probability pass, dibs.py:179-181)
     TRY(launch_prologue(p, q.x_next, p->ld, p->M_loc, p->row0, nullptr, nullptr, 0, 0u, p->scores, nullptr, stream));
     mark(p, stream, DIBS_PHASE_STEP_KEYS);
@@ -1515,7 +1575,10 @@ static int hook_pair(dibs_plan* p, const float* z, const float* theta, const flo
         TRY(sc.get(&part, (size_t)n * D));
         q.phi_part = part;
         q.phi_out = phi; q.phi_ld = D;            // phi only: no optimizer step (x_next == null)
-        TRY(launch_phi(p, q, stream));
+        PhiMmaMaps mm;
+        const bool mma = phi_mma_eligible(n, D);
+        if (mma) TRY(fill_mma_maps(mm, kf, kz, p->Dth ? kt : nullptr, n, n, xs, gs, D));
+        TRY(launch_phi(p, q, stream, mma ? &mm : nullptr));
         CU(cudaMemcpy2DAsync(phi_z, fz, phi, fd, fz, n, cudaMemcpyDeviceToDevice, stream));
         if (phi_th && p->Dth) CU(cudaMemcpy2DAsync(phi_th, ft, phi + p->Dz, fd, ft, n, cudaMemcpyDeviceToDevice, stream));
     }

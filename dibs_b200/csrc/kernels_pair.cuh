@@ -157,6 +157,101 @@ __global__ void __launch_bounds__(256) k_pair_finish(PairParams p) {
 // several GPUs -- stores the updated block into every peer's next particle buffer (fused exchange).
 constexpr int PT_C = 64, PT_J = 32;
 
+// Epilogue of the phi pass for one output tile -- rows [i0, i0 + tile_rows) of the rank's slab x the (up to) 64 columns
+// [c0, c_end) -- run by ALL threads of the tile's last-arriving j-slice CTA (SIMT and tensor-core kernels alike):
+// fixed-order sum of the slice planes -> phi = -(sum)/M (svgd.py:212-216), RMSprop / SGD step (svgd.py:265,718-719;
+// jax.example_libraries.optimizers), updated rows to this rank's next buffer and -- on several GPUs -- to every
+// peer's.  16 consecutive threads cover one row's 64 columns: 128-bit accesses, 256 contiguous bytes per row.
+__device__ __forceinline__ void phi_finish_tile(const PairParams& p, int i0, int tile_rows, int c0, int c_end, int tid, int nthr) {
+    const int D = p.dz + p.dth;
+    const size_t plane = (size_t)p.n_rows * D;
+    const float inv_m = 1.0f / (float)p.n_all;
+    for (int idx = tid; idx < tile_rows * 16; idx += nthr) {
+        const int gi = i0 + (idx >> 4), gc = c0 + (idx & 15) * 4;
+        if (gi >= p.n_rows || gc >= c_end) continue;
+        const bool full = gc + 3 < c_end;
+        float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        const float* pr = p.phi_part + (size_t)gi * D + gc;
+        if (full && ((plane | ((size_t)gi * D + gc)) & 3) == 0) {
+#pragma unroll 8
+            for (int s = 0; s < p.n_jsplit; ++s) {
+                const float4 v4 = __ldcg(reinterpret_cast<const float4*>(pr + (size_t)s * plane));
+                sum[0] += v4.x; sum[1] += v4.y; sum[2] += v4.z; sum[3] += v4.w;
+            }
+        } else {
+            for (int s = 0; s < p.n_jsplit; ++s) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (gc + u < c_end) sum[u] += __ldcg(pr + (size_t)s * plane + u);
+            }
+        }
+        const float* xr = p.x_all + (size_t)(p.row0 + gi) * p.ld + gc;
+        float xc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (full && ((reinterpret_cast<uintptr_t>(xr) & 15) == 0)) {
+            const float4 x4 = *reinterpret_cast<const float4*>(xr);
+            xc[0] = x4.x; xc[1] = x4.y; xc[2] = x4.z; xc[3] = x4.w;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (gc + u < c_end) xc[u] = xr[u];
+        }
+        float phi[4], xn[4], vn[4];
+        float* vp = p.v ? p.v + (size_t)gi * p.v_ld + gc : nullptr;
+        const bool vec_v = full && p.x_next && p.optimizer == 1 && ((((size_t)gi * p.v_ld + gc) & 3) == 0);
+        float vo[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (p.x_next && p.optimizer == 1) {
+            if (vec_v) { const float4 v4 = *reinterpret_cast<const float4*>(vp); vo[0] = v4.x; vo[1] = v4.y; vo[2] = v4.z; vo[3] = v4.w; }
+            else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (gc + u < c_end) vo[u] = vp[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            // -(weighted_gradient_ascent + repulsion).mean(axis=0)   (svgd.py:212-216)
+            phi[u] = -sum[u] * inv_m;
+            if (p.optimizer == 1) {
+                // rmsprop(step, gamma=0.9, eps=1e-8): v = v*gamma + g^2*(1-gamma); x -= step*g/sqrt(v+eps)
+                vn[u] = __fadd_rn(__fmul_rn(vo[u], 0.9f), __fmul_rn(__fmul_rn(phi[u], phi[u]), 0.1f));
+                xn[u] = __fsub_rn(xc[u], __fdiv_rn(__fmul_rn(p.stepsize, phi[u]), __fsqrt_rn(__fadd_rn(vn[u], 1e-8f))));
+            } else {
+                vn[u] = 0.0f;
+                xn[u] = __fsub_rn(xc[u], __fmul_rn(p.stepsize, phi[u]));   // sgd: x - step * g
+            }
+        }
+        if (p.phi_out) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (gc + u < c_end) p.phi_out[(size_t)gi * p.phi_ld + gc + u] = phi[u];
+        }
+        if (p.x_next) {
+            if (p.optimizer == 1) {
+                if (vec_v) *reinterpret_cast<float4*>(vp) = make_float4(vn[0], vn[1], vn[2], vn[3]);
+                else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (gc + u < c_end) vp[u] = vn[u];
+                }
+            }
+            const size_t off_loc = (size_t)gi * p.next_ld + gc;                    // in this rank's rows
+            const size_t off_all = (size_t)(p.row0 + gi) * p.next_ld + gc;         // in a whole particle buffer
+            if (full && (((uintptr_t)(p.x_next + off_loc)) & 15) == 0) {
+                const float4 x4 = make_float4(xn[0], xn[1], xn[2], xn[3]);
+                *reinterpret_cast<float4*>(p.x_next + off_loc) = x4;
+                if (p.push_x.world) {
+#pragma unroll 1
+                    for (int q = 0; q < p.push_x.world; ++q)
+                        if (q != p.push_x.rank) *reinterpret_cast<float4*>(p.push_x.dst[q] + off_all) = x4;
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (gc + u >= c_end) continue;
+                    p.x_next[off_loc + u] = xn[u];
+                    if (p.push_x.world) peer_store(p.push_x, off_all + u, xn[u]);
+                }
+            }
+        }
+    }
+}
+
 template <int RPT>
 __global__ void __launch_bounds__(128) k_phi(PairParams p) {
     constexpr int PB_I = 8 * RPT;       // rows per tile
@@ -280,86 +375,7 @@ __global__ void __launch_bounds__(128) k_phi(PairParams p) {
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const float inv_m = 1.0f / (float)p.n_all;
-    // a thread's 4 columns move as one 128-bit access wherever the row layout allows (always, for the plan's own
-    // buffers when dz is a multiple of 4): the peer stores of a warp then cover two rows x 256 contiguous bytes
-    const bool full = gc + 3 < c_end;
-#pragma unroll 2
-    for (int a = 0; a < RPT; ++a) {
-        const int gi = i0 + ty * RPT + a;
-        if (gi >= p.n_rows) continue;
-        float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        const float* pr = p.phi_part + (size_t)gi * D + gc;
-        if (full && ((plane | ((size_t)gi * D + gc)) & 3) == 0) {
-#pragma unroll 8
-            for (int s = 0; s < p.n_jsplit; ++s) {
-                const float4 v4 = __ldcg(reinterpret_cast<const float4*>(pr + (size_t)s * plane));
-                sum[0] += v4.x; sum[1] += v4.y; sum[2] += v4.z; sum[3] += v4.w;
-            }
-        } else {
-            for (int s = 0; s < p.n_jsplit; ++s) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (gc + u < c_end) sum[u] += __ldcg(pr + (size_t)s * plane + u);
-            }
-        }
-        const float xc[4] = {lo2(xi[a][0]), hi2(xi[a][0]), lo2(xi[a][1]), hi2(xi[a][1])};
-        float phi[4], xn[4], vn[4];
-        float* vp = p.v ? p.v + (size_t)gi * p.v_ld + gc : nullptr;
-        const bool vec_v = full && p.x_next && p.optimizer == 1 && ((((size_t)gi * p.v_ld + gc) & 3) == 0);
-        float vo[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        if (p.x_next && p.optimizer == 1) {
-            if (vec_v) { const float4 v4 = *reinterpret_cast<const float4*>(vp); vo[0] = v4.x; vo[1] = v4.y; vo[2] = v4.z; vo[3] = v4.w; }
-            else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) if (gc + u < c_end) vo[u] = vp[u];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            // -(weighted_gradient_ascent + repulsion).mean(axis=0)   (svgd.py:212-216)
-            phi[u] = -sum[u] * inv_m;
-            if (p.optimizer == 1) {
-                // rmsprop(step, gamma=0.9, eps=1e-8): v = v*gamma + g^2*(1-gamma); x -= step*g/sqrt(v+eps)
-                vn[u] = __fadd_rn(__fmul_rn(vo[u], 0.9f), __fmul_rn(__fmul_rn(phi[u], phi[u]), 0.1f));
-                xn[u] = __fsub_rn(xc[u], __fdiv_rn(__fmul_rn(p.stepsize, phi[u]), __fsqrt_rn(__fadd_rn(vn[u], 1e-8f))));
-            } else {
-                vn[u] = 0.0f;
-                xn[u] = __fsub_rn(xc[u], __fmul_rn(p.stepsize, phi[u]));   // sgd: x - step * g
-            }
-        }
-        if (p.phi_out) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) if (gc + u < c_end) p.phi_out[(size_t)gi * p.phi_ld + gc + u] = phi[u];
-        }
-        if (p.x_next) {
-            if (p.optimizer == 1) {
-                if (vec_v) *reinterpret_cast<float4*>(vp) = make_float4(vn[0], vn[1], vn[2], vn[3]);
-                else {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) if (gc + u < c_end) vp[u] = vn[u];
-                }
-            }
-            const size_t off_loc = (size_t)gi * p.next_ld + gc;                    // in this rank's rows
-            const size_t off_all = (size_t)(p.row0 + gi) * p.next_ld + gc;         // in a whole particle buffer
-            if (full && (((uintptr_t)(p.x_next + off_loc)) & 15) == 0) {
-                const float4 x4 = make_float4(xn[0], xn[1], xn[2], xn[3]);
-                *reinterpret_cast<float4*>(p.x_next + off_loc) = x4;
-                if (p.push_x.world) {
-#pragma unroll 1
-                    for (int q = 0; q < p.push_x.world; ++q)
-                        if (q != p.push_x.rank) *reinterpret_cast<float4*>(p.push_x.dst[q] + off_all) = x4;
-                }
-            } else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (gc + u >= c_end) continue;
-                    p.x_next[off_loc + u] = xn[u];
-                    if (p.push_x.world) peer_store(p.push_x, off_all + u, xn[u]);
-                }
-            }
-        }
-    }
+    phi_finish_tile(p, i0, PB_I, c0, c_end, tid, 128);
     if (p.push_x.world) peer_signal(p.push_x, gridDim.x * gridDim.y);      // one signal per output tile
 }
 

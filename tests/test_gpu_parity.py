@@ -503,3 +503,40 @@ def test_device_other_than_current():
     assert r1[0].device.index == 1
     assert torch.equal(m0._last_state["z"].cpu(), m1._last_state["z"].cpu())
     assert torch.equal(r0[0].cpu(), r1[0].cpu())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tensor-core phi (kernels_phi_mma.cuh: tcgen05 3 x TF32, TMA-staged operands) -- taken for >= 128 particles
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lik,n,spread", [("lingauss", 256, 1.0), ("bge", 384, 1.0), ("lingauss", 136, 0.02), ("densenn", 128, 1.0)])
+def test_phi_tensor_core_path(lik, n, spread):
+    """phi_z / phi_theta of n >= 128 particles (the tcgen05 kernel: GEMM-form repulsion, split-precision products) against
+    the DIFFERENCE-form oracle (svgd.py:194-224, 591-670) in fp64, at 1e-5 of the largest entry per block -- including a
+    tightly clustered particle set (spread = 0.02), where the GEMM form cancels the most."""
+    from dibs_b200.inference import PRNGKey
+    d = 20
+    g = _mid_case(lik, d=d, m=n, s=8, a=4)
+    model = build_model(g, sample_case=True)
+    cfg = oracle_config(g, sample_case=True)
+    st = orc.init_particles(cfg, PRNGKey(6), n, None, np.float32)
+    rng = np.random.default_rng(4)
+    # particles = a common centre + spread * individual offsets; gradients of the magnitude the step produces
+    z = (st.z[:1] + spread * st.z).astype(np.float32)
+    th = None if st.theta is None else (st.theta[:1] + spread * st.theta).astype(np.float32)
+    gz = (rng.normal(size=z.shape) * 30.0).astype(np.float32)
+    gth = None if th is None else (rng.normal(size=th.shape) * 30.0).astype(np.float32)
+    k_full, k_z, k_t = orc.kernel_matrix(cfg, z.astype(np.float64), None if th is None else th.astype(np.float64), np.float64)
+    ref_z = orc.phi_update(k_full, k_z, cfg.h_latent, z.astype(np.float64), gz.astype(np.float64), np.float64)
+    phi_z, phi_t = model._parallel_update(z, th, gz, gth)
+    got_z = npy(phi_z).astype(np.float64)
+    assert np.abs(got_z - ref_z).max() <= 1e-5 * np.abs(ref_z).max() + 1e-7, ("phi_z", np.abs(got_z - ref_z).max(), np.abs(ref_z).max())
+    if th is not None:
+        ref_t = orc.phi_update(k_full, k_t, cfg.h_theta, th.astype(np.float64), gth.astype(np.float64), np.float64)
+        got_t = npy(phi_t).astype(np.float64)
+        assert np.abs(got_t - ref_t).max() <= 1e-5 * np.abs(ref_t).max() + 1e-7, ("phi_theta", np.abs(got_t - ref_t).max(), np.abs(ref_t).max())
+    # the repulsion term alone (zero gradients): where the GEMM form's cancellation would show
+    zero_t = None if th is None else np.zeros_like(th)
+    rep_z, rep_t = model._parallel_update(z, th, np.zeros_like(z), zero_t)
+    ref_rz = orc.phi_update(k_full, k_z, cfg.h_latent, z.astype(np.float64), np.zeros_like(z, np.float64), np.float64)
+    err = np.abs(npy(rep_z).astype(np.float64) - ref_rz).max()
+    assert err <= 1e-5 * np.abs(ref_z).max() + 1e-7, ("repulsion z", err, np.abs(ref_rz).max(), np.abs(ref_z).max())

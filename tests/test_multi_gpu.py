@@ -56,7 +56,7 @@ def test_sample_bit_identical_across_gpus(world, tmp_path):
     out = str(tmp_path)
     _run(1, out, {})
     _run(world, out, {"MGPU_EXPECT": "peer-memory"})
-    _compare(out, world, ("bge", "lin", "nn"))
+    _compare(out, world, ("bge", "lin", "nn", "linL"))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
@@ -70,6 +70,6 @@ def test_sample_bit_identical_nccl_fallback(tmp_path):
 def test_two_ranks_one_gpu_peer_memory(tmp_path):
     """2 ranks sharing cuda:0: the sharded step over CUDA-IPC peer memory vs the single-rank run, bit for bit."""
     out = str(tmp_path)
-    _run(1, out, {"MGPU_CASES": "lin,bge"})
-    _run(2, out, {"MGPU_CASES": "lin,bge", "MGPU_SAME_GPU": "1", "MGPU_EXPECT": "peer-memory"})
-    _compare(out, 2, ("lin", "bge"))
+    _run(1, out, {"MGPU_CASES": "lin,bge,linL"})
+    _run(2, out, {"MGPU_CASES": "lin,bge,linL", "MGPU_SAME_GPU": "1", "MGPU_EXPECT": "peer-memory"})
+    _compare(out, 2, ("lin", "bge", "linL"))

@@ -13,7 +13,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.environ.get("MGPU_OUT") or os.path.join(ROOT, "gpurun_out")
-CASES = {"lin": dict(d=20, m=64, s=32, steps=7), "bge": dict(d=12, m=32, s=16, steps=5), "nn": dict(d=10, m=16, s=8, steps=4)}
+CASES = {"lin": dict(d=20, m=64, s=32, steps=7), "bge": dict(d=12, m=32, s=16, steps=5), "nn": dict(d=10, m=16, s=8, steps=4),
+         # >= 128 particles: the tensor-core phi kernel (its choice depends on the GLOBAL particle count only)
+         "linL": dict(d=12, m=256, s=8, steps=3)}
 
 
 def run():
@@ -41,12 +43,12 @@ def run():
         else:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     os.makedirs(OUT, exist_ok=True)
-    for name in os.environ.get("MGPU_CASES", "bge,lin,nn").split(","):
+    for name in os.environ.get("MGPU_CASES", "bge,lin,nn,linL").split(","):
         c = CASES[name]
         d = c["d"]
         x = make_linear_gaussian_data(seed=1, n_vars=d, n_observations=50)["x"]
         gm = ErdosReniDAGDistribution(n_vars=d)
-        if name == "lin":
+        if name in ("lin", "linL"):
             model = JointDiBS(x=x, graph_model=gm, likelihood_model=LinearGaussian(n_vars=d), n_grad_mc_samples=c["s"])
         elif name == "nn":
             model = JointDiBS(x=x, graph_model=gm, likelihood_model=DenseNonlinearGaussian(n_vars=d, hidden_layers=(5,)),
@@ -70,7 +72,7 @@ def run():
 
 def compare(w):
     ok = True
-    for name in CASES:
+    for name in os.environ.get("MGPU_CASES", "bge,lin,nn,linL").split(","):
         a = np.load(os.path.join(OUT, f"mgpu_w1_{name}.npz"))
         b = np.load(os.path.join(OUT, f"mgpu_w{w}_{name}.npz"))
         for k in ("z", "theta"):
