@@ -441,7 +441,8 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 // fp32 row-major matrix [rows][cols] with row stride `ld` floats; box = 32 columns (one 128-byte swizzle row) x box_rows
-static int make_map(CUtensorMap* m, const float* base, size_t rows, size_t cols, size_t ld, unsigned box_rows) {
+static int make_map(CUtensorMap* m, const float* base, size_t rows, size_t cols, size_t ld, unsigned box_rows,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(DIBS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -449,7 +450,7 @@ static int make_map(CUtensorMap* m, const float* base, size_t rows, size_t cols,
     cuuint32_t box[2] = {32u, box_rows};
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DIBS_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return DIBS_OK;
 }
@@ -462,8 +463,9 @@ static int fill_mma_maps(PhiMmaMaps& mm, const float* kfull, const float* kz, co
     TRY(make_map(&mm.a_full, kfull, n_rows, n_all, n_all, MM_ROWS));
     TRY(make_map(&mm.a_z, kz, n_rows, n_all, n_all, MM_ROWS));
     TRY(make_map(&mm.a_t, kt ? kt : kz, n_rows, n_all, n_all, MM_ROWS));
-    TRY(make_map(&mm.b_x, x_all, n_all, ld, ld, MM_KS));
-    TRY(make_map(&mm.b_g, g_all, n_all, ld, ld, MM_KS));
+    // MN-major 32-bit operands: 32-byte swizzle atoms (see kernels_phi_mma.cuh)
+    TRY(make_map(&mm.b_x, x_all, n_all, ld, ld, MM_KS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    TRY(make_map(&mm.b_g, g_all, n_all, ld, ld, MM_KS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     return DIBS_OK;
 }
 
@@ -866,14 +868,7 @@ static int stream_edge(cudaStream_t from, cudaStream_t to, cudaEvent_t ev) {
 
 static int ensure_aux(dibs_plan* p) {
     for (int i = 0; i < 3; ++i) {
-        if (!p->aux[i]) {
-            // EXPERIMENT knob DIBS_X_PRIO: sibling branches at high priority, so that the MAIN branch's kernel finishes
-            // last and the join in front of phi is not a cross-branch edge on the critical path
-            static const int x_prio = getenv("DIBS_X_PRIO") ? atoi(getenv("DIBS_X_PRIO")) : 0;
-            int least = 0, greatest = 0;
-            CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-            CU(cudaStreamCreateWithPriority(&p->aux[i], cudaStreamNonBlocking, x_prio ? greatest : least));
-        }
+        if (!p->aux[i]) CU(cudaStreamCreateWithFlags(&p->aux[i], cudaStreamNonBlocking));
         if (!p->ev_join[i]) CU(cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < 2; ++i) if (!p->ev_fork[i]) CU(cudaEventCreateWithFlags(&p->ev_fork[i], cudaEventDisableTiming));
@@ -905,11 +900,10 @@ static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_st
     fuse.total = (joint ? sh.chunks : 0) + sh.chunks + a.acyc_chunks;
 
     McParams q;
-    static const int x_acyc_inline = getenv("DIBS_X_ACYC_INLINE") ? atoi(getenv("DIBS_X_ACYC_INLINE")) : 0;   // EXPERIMENT
-    cudaStream_t s_th = conc ? p->aux[0] : stream, s_ac = (conc && !x_acyc_inline) ? p->aux[1] : stream;
+    cudaStream_t s_th = conc ? p->aux[0] : stream, s_ac = conc ? p->aux[1] : stream;
     if (conc) {
         CU(cudaEventRecord(p->ev_fork[1], stream));
-        if (joint) CU(cudaStreamWaitEvent(s_th, p->ev_fork[1], 0));
+        if (joint && s_th != stream) CU(cudaStreamWaitEvent(s_th, p->ev_fork[1], 0));
         if (s_ac != stream) CU(cudaStreamWaitEvent(s_ac, p->ev_fork[1], 0));
     }
     if (joint) {
@@ -930,7 +924,7 @@ static int enqueue_grads(dibs_plan* p, const Src& s, float* th_acc, float* th_st
     TRY(launch_acyc(p, s, joint ? 2 : 1, acyc, s_ac, &fuse));
     mark(p, s_ac, DIBS_PHASE_ACYCLIC);
     if (conc) {
-        if (joint) TRY(stream_edge(s_th, stream, p->ev_join[0]));
+        if (joint && s_th != stream) TRY(stream_edge(s_th, stream, p->ev_join[0]));
         if (s_ac != stream) TRY(stream_edge(s_ac, stream, p->ev_join[1]));
     }
     return DIBS_OK;
@@ -1032,8 +1026,7 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream, bool conc) {
     // the kernel matrix needs the particles only: it runs on a side branch under the gradient phase.  On several GPUs
     // the rows every rank updated at the end of the previous step were stored into this rank's buffer by the peers'
     // phi kernels (the distance kernel waits on their flags) or, on the NCCL path, arrive by an all-gather here
-    static const int x_pair_inline = getenv("DIBS_X_PAIR_INLINE") ? atoi(getenv("DIBS_X_PAIR_INLINE")) : 0;   // EXPERIMENT
-    cudaStream_t s_k = (conc && !x_pair_inline) ? p->aux[2] : stream;
+    cudaStream_t s_k = conc ? p->aux[2] : stream;
     if (conc && s_k != stream) TRY(stream_edge(stream, s_k, p->ev_fork[0]));
     if (multi && !p->p2p) {
         NC(g_nccl.AllGather(loc, P, (size_t)p->M_loc * p->ld, /*ncclFloat32*/ 7, p->comm_x, s_k));

@@ -7,9 +7,9 @@
 // with K = K_z + K_theta (drive term) and K* = K_z for the Z block, K_theta for the Theta block (repulsion).
 //
 // Why split precision: TF32 keeps 11 significand bits; parity with the fp32 reference (1e-5) needs ~fp32 products.
-// Every operand x is split exactly into hi = x with the low 13 mantissa bits cleared (a TF32 number) and
-// lo = x - hi (at most 13 significant bits); a b ~= hi_a hi_b + hi_a lo_b + lo_a hi_b, error ~2^-22 |a b|, all three
-// products accumulated in fp32 in TMEM.  The repulsion term is evaluated in GEMM form (K* X minus the row sum times
+// Every operand x is split exactly into hi = x rounded to the nearest TF32 value and lo = x - hi (at most 12
+// significant bits); a b ~= hi_a hi_b + hi_a lo_b + lo_a hi_b, error ~2^-23 |a b|, all three products accumulated in
+// fp32 in TMEM.  The repulsion term is evaluated in GEMM form (K* X minus the row sum times
 // x_i); its cancellation only bites when every particle a row has weight on sits within ~1e-4 of it, where the term
 // itself vanishes against the drive term (checked against the difference-form oracle in tests/test_gpu_parity.py).
 //
@@ -23,9 +23,11 @@
 // Shared-memory operand layouts are the canonical 128-byte-swizzled ones a plain 2-D TMA box produces:
 //   A = K tiles, K-major:   [128 rows][32 j] fp32, rows of 128 B, 16-byte chunks XOR-swizzled by (row & 7);
 //                           UMMA descriptor: SWIZZLE_128B, SBO = 1024 B (8 rows), K step of 8 = +32 B.
-//   B = G / X tiles, MN-major: two panels of [32 j][32 columns] fp32 (rows of 128 B, same swizzle);
-//                           UMMA descriptor: SWIZZLE_128B, LBO = 4096 B (next 32-column panel), SBO = 1024 B (next
-//                           8 j), K step of 8 = +1024 B.
+//   B = G / X tiles, MN-major: two panels of [32 j][32 columns] fp32, rows of 128 B, 32-byte chunks XOR-swizzled by
+//                           (j & 3) (TMA mode SWIZZLE_128B_ATOM_32B): for an MN-major 32-bit operand the tensor core
+//                           accepts only this layout (UMMA SWIZZLE_128B_BASE32B; with plain SWIZZLE_128B the MMAs
+//                           silently contribute zeros -- found the hard way); LBO = 4096 B (next 32-column panel),
+//                           SBO = 512 B (next 4 j), K step of 8 = +1024 B.
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
@@ -105,27 +107,34 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start address, LBO, SBO in 16-byte units, version 1
-// (Blackwell), layout type 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// (Blackwell), layout type 2 = SWIZZLE_128B (16-byte chunks XORed with the row, K-major A), 1 = SWIZZLE_128B_BASE32B
+// (32-byte chunks XORed with row & 3 -- the only layout the tensor core accepts for an MN-major 32-bit operand)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= (uint64_t)1 << 46;       // version_
-    d |= (uint64_t)2 << 61;       // layout_type_ = SWIZZLE_128B
+    d |= (uint64_t)layout_type << 61;
     return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return umma_desc(smem_addr, lbo_bytes, sbo_bytes, 2u);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, TF32 x TF32, A K-major, B MN-major, N, M
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// x -> (hi, lo): hi = x with the 13 low mantissa bits cleared (exactly a TF32 value), lo = x - hi (exact in fp32)
+// x -> (hi, lo): hi = x rounded to the nearest TF32 value (13 low mantissa bits zero: the tensor core reads it exactly
+// whatever its own conversion does), lo = x - hi, exact in fp32 and at most 12 significant bits.
+// Measured against fp64 on the phi contraction: 3 products ~2e-6 of the largest entry; hi x hi alone 2e-3.
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void split_tf32(float4 v, float4& hi, float4& lo) {
-    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
-    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
-    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
-    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
+    hi.x = tf32_rn(v.x); lo.x = v.x - hi.x;
+    hi.y = tf32_rn(v.y); lo.y = v.y - hi.y;
+    hi.z = tf32_rn(v.z); lo.z = v.z - hi.z;
+    hi.w = tf32_rn(v.w); lo.w = v.w - hi.w;
 }
 
 __global__ void __launch_bounds__(MM_THREADS, 1)
@@ -212,9 +221,10 @@ k_phi_mma(const __grid_constant__ PairParams p, const __grid_constant__ PhiMmaMa
                     // A: K-major, +32 B per K step inside the 128-byte swizzle row; SBO = 8 rows
                     const uint64_t da1h = umma_desc_sw128(a1h + 32 * ks, 16, 1024), da1l = umma_desc_sw128(a1l + 32 * ks, 16, 1024);
                     const uint64_t da2h = umma_desc_sw128(a2h + 32 * ks, 16, 1024), da2l = umma_desc_sw128(a2l + 32 * ks, 16, 1024);
-                    // B: MN-major, +1024 B per K step (8 rows of 128 B); LBO = next 32-column panel, SBO = next 8 j
-                    const uint64_t db1h = umma_desc_sw128(b1h + 1024 * ks, MM_B_BYTES / 2, 1024), db1l = umma_desc_sw128(b1l + 1024 * ks, MM_B_BYTES / 2, 1024);
-                    const uint64_t db2h = umma_desc_sw128(b2h + 1024 * ks, MM_B_BYTES / 2, 1024), db2l = umma_desc_sw128(b2l + 1024 * ks, MM_B_BYTES / 2, 1024);
+                    // B: MN-major (SWIZZLE_128B_BASE32B atoms of 4 j x 128 B), +1024 B per K step (8 rows of 128 B);
+                    // LBO = next 32-column panel, SBO = next 4 j
+                    const uint64_t db1h = umma_desc(b1h + 1024 * ks, MM_B_BYTES / 2, 512, 1u), db1l = umma_desc(b1l + 1024 * ks, MM_B_BYTES / 2, 512, 1u);
+                    const uint64_t db2h = umma_desc(b2h + 1024 * ks, MM_B_BYTES / 2, 512, 1u), db2l = umma_desc(b2l + 1024 * ks, MM_B_BYTES / 2, 512, 1u);
                     tc_mma_tf32(d1, da1h, db1h, idesc, acc);      // K G
                     tc_mma_tf32(d1, da1h, db1l, idesc, 1u);
                     tc_mma_tf32(d1, da1l, db1h, idesc, 1u);
