@@ -161,6 +161,7 @@ struct dibs_plan {
     // and gradient buffers; chosen by the GLOBAL particle count only, so every world size takes the same arithmetic
     bool phi_mma = false;
     PhiMmaMaps mma_maps[2];
+    float* k_split = nullptr;      // [6][M_loc][M] TF32 hi / lo parts of K, K_z, K_theta (k_pair_finish)
     // CUDA graphs of one step, per buffer parity
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
     int kernels_per_step = 0;
@@ -261,7 +262,10 @@ static McShape mc_shape_for(bool qr, int likelihood, int d, int hidden, int n_lo
         sh.gpb = best;
         sh.threads = ((best * d) + 31) / 32 * 32;
         const int rounds = ceil_div(Q, best);
-        int chunks = ceil_div(mc_target_ctas(8), n_local);
+        // up to 8 chunks per particle whatever the number of particles a rank owns: the chunking fixes the order in which
+        // the online-softmax partials are merged, so it must not depend on the rank count (bit-identical results)
+        int chunks = 8;
+        (void)n_local;
         if (chunks > rounds) chunks = rounds;
         if (chunks < 1) chunks = 1;
         const int rpc = ceil_div(rounds, chunks);
@@ -328,6 +332,8 @@ static McShape mc_shape_dense(int d, int n_local, int S, bool pair_ok = false) {
     sh.threads = ((dense_nt(d) + 31) / 32) * 32;
     return sh;
 }
+
+static bool phi_mma_eligible(int n_all, int ld, int min_particles);
 
 extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
     if (!cfg || !out) return fail(DIBS_ERR_INVALID_ARG, "null argument");
@@ -398,8 +404,10 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
     // pairwise: split the feature axis until the distance pass has >= ~2 x 148 CTAs; Z and Theta features are cut
     // separately so that a split never straddles the Z | Theta boundary
     {
-        int tiles = ceil_div(p->M, KT) * ceil_div(p->M_loc, KT);
-        int ns = ceil_div(2 * 148, tiles);
+        // the split is a function of (M, D) only -- sized for the 8-way sharded case -- so K, and everything downstream,
+        // is bit-identical for any number of ranks
+        int tiles = ceil_div(p->M, KT) * ceil_div(p->M, KT);
+        int ns = ceil_div(8 * 2 * 148, tiles);
         int max_ns = ceil_div(p->D, 2 * KF);
         if (ns > max_ns) ns = max_ns;
         if (ns < 1) ns = 1;
@@ -421,6 +429,13 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
         if (ns < 1) ns = 1;
         p->j_len = ceil_div(ceil_div(p->M, ns), PT_J) * PT_J;
         p->n_jsplit = ceil_div(p->M, p->j_len);
+        // tensor-core phi (>= MMA_MIN_PARTICLES particles, see phi_mma_eligible): a CTA pays a fixed pipeline fill /
+        // TMEM / epilogue cost, so slices are long -- 512 particles, again a function of M only
+        const int ld_rows = (p->D + 3) & ~3;
+        if (phi_mma_eligible(p->M, ld_rows, 512)) {
+            p->j_len = 512;
+            p->n_jsplit = ceil_div(p->M, p->j_len);
+        }
     }
     *out = p;
     return DIBS_OK;
@@ -454,15 +469,18 @@ static int make_map(CUtensorMap* m, const float* base, size_t rows, size_t cols,
     if (r != CUDA_SUCCESS) return fail(DIBS_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return DIBS_OK;
 }
-static bool phi_mma_eligible(int n_all, int ld) {
+// The tensor-core kernel is taken from MMA_MIN_PARTICLES particles on (a function of the GLOBAL count, so every world
+// size runs the same arithmetic): below that its 128-row x 64-column tiles are too few to fill 148 SMs and the SIMT
+// kernel wins (measured at 256 particles: 67 vs 39 us).
+constexpr int MMA_MIN_PARTICLES = 512;
+static bool phi_mma_eligible(int n_all, int ld, int min_particles = MMA_MIN_PARTICLES) {
     static const bool off = getenv("DIBS_B200_PHI_SIMT") && getenv("DIBS_B200_PHI_SIMT")[0] == '1';      // debugging: SIMT phi everywhere
-    return !off && n_all >= 128 && (n_all % 4) == 0 && (ld % 4) == 0;
+    return !off && n_all >= min_particles && (n_all % 4) == 0 && (ld % 4) == 0;
 }
-static int fill_mma_maps(PhiMmaMaps& mm, const float* kfull, const float* kz, const float* kt, int n_rows, int n_all,
+static int fill_mma_maps(PhiMmaMaps& mm, const float* k_split, bool has_theta, int n_rows, int n_all,
                          const float* x_all, const float* g_all, int ld) {
-    TRY(make_map(&mm.a_full, kfull, n_rows, n_all, n_all, MM_ROWS));
-    TRY(make_map(&mm.a_z, kz, n_rows, n_all, n_all, MM_ROWS));
-    TRY(make_map(&mm.a_t, kt ? kt : kz, n_rows, n_all, n_all, MM_ROWS));
+    const size_t plane = (size_t)n_rows * n_all;
+    for (int i = 0; i < 6; ++i) TRY(make_map(&mm.a[i], k_split + (size_t)((i < 4 || has_theta) ? i : i - 2) * plane, n_rows, n_all, n_all, MM_ROWS));
     // MN-major 32-bit operands: 32-byte swizzle atoms (see kernels_phi_mma.cuh)
     TRY(make_map(&mm.b_x, x_all, n_all, ld, ld, MM_KS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     TRY(make_map(&mm.b_g, g_all, n_all, ld, ld, MM_KS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
@@ -513,9 +531,11 @@ static int ensure_step_ws(dibs_plan* p) {
         (r = alloc((void**)&p->phi_part, (size_t)p->n_jsplit * p->M_loc * p->D * sizeof(float))))
         return r;
     p->phi_mma = phi_mma_eligible(p->M, p->ld);
-    if (p->phi_mma)
+    if (p->phi_mma) {
+        if ((r = alloc((void**)&p->k_split, 6 * plane))) return r;
         for (int par = 0; par < 2; ++par)
-            TRY(fill_mma_maps(p->mma_maps[par], p->kfull, p->kz, p->Dth ? p->kt : nullptr, p->M_loc, p->M, p->pk[par], p->gk[par], p->ld));
+            TRY(fill_mma_maps(p->mma_maps[par], p->k_split, p->Dth > 0, p->M_loc, p->M, p->pk[par], p->gk[par], p->ld));
+    }
     p->step_ws = true;
     return DIBS_OK;
 }
@@ -556,7 +576,7 @@ extern "C" int dibs_plan_destroy(dibs_plan* p) {
     for (int i = 0; i < 3; ++i) { if (p->aux[i]) cudaStreamDestroy(p->aux[i]); if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]); }
     for (int i = 0; i < 2; ++i) if (p->ev_fork[i]) cudaEventDestroy(p->ev_fork[i]);
     if (p->peer_error) cudaFreeHost(p->peer_error);
-    void* ptrs[] = {p->summary_ws, p->arrive, p->phi_cnt, p->rx_dense, p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->gk[0], p->gk[1], p->peer_flags_local, p->peer_epoch, p->peer_counter, p->v, p->base, p->st, p->step_keys, p->scores,
+    void* ptrs[] = {p->summary_ws, p->arrive, p->phi_cnt, p->k_split, p->rx_dense, p->x, p->mask, p->bge_r, p->bge_table, p->bge_coef, p->pk[0], p->pk[1], p->gk[0], p->gk[1], p->peer_flags_local, p->peer_epoch, p->peer_counter, p->v, p->base, p->st, p->step_keys, p->scores,
                     p->th_acc, p->th_stats, p->z_acc, p->z_stats, p->acyc, p->dist_part, p->kz, p->kt, p->kfull, p->phi_part};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
@@ -936,6 +956,7 @@ static void fill_pair(const dibs_plan* p, PairParams& q) {
     q.n_split = p->n_split; q.n_split_z = p->n_split_z; q.split_len_z = p->split_len_z; q.split_len_t = p->split_len_t;
     q.dist_part = p->dist_part;
     q.kz = p->kz; q.kt = p->Dth ? p->kt : nullptr; q.kfull = p->kfull;
+    q.k_split = p->phi_mma ? p->k_split : nullptr;
     q.h_z = p->cfg.h_latent; q.h_t = p->cfg.h_theta; q.scale_z = p->cfg.scale_latent; q.scale_t = p->cfg.scale_theta;
     q.n_jsplit = p->n_jsplit; q.j_len = p->j_len; q.phi_part = p->phi_part; q.phi_cnt = p->phi_cnt;
     q.optimizer = p->cfg.optimizer; q.stepsize = p->cfg.stepsize;
@@ -1560,6 +1581,10 @@ static int hook_pair(dibs_plan* p, const float* z, const float* theta, const flo
     if (!k_out) TRY(sc.get(&kf, plane)); else kf = k_out;
     q.dist_part = dist; q.kz = kz; q.kt = p->Dth ? kt : nullptr; q.kfull = kf;
     q.x_all = xs; q.ld = D; q.g_all = gs; q.g_ld = D;
+    const bool mma = phi_z && phi_mma_eligible(n, D, 128);     // hooks: from 128 particles, so the parity tests reach the kernel cheaply
+    float* ksp = nullptr;
+    if (mma) TRY(sc.get(&ksp, 6 * plane));
+    q.k_split = ksp;
     TRY(launch_kmat(p, q, stream));
     if (phi_z) {
         TRY(sc.get(&phi, (size_t)n * D));
@@ -1569,8 +1594,7 @@ static int hook_pair(dibs_plan* p, const float* z, const float* theta, const flo
         q.phi_part = part;
         q.phi_out = phi; q.phi_ld = D;            // phi only: no optimizer step (x_next == null)
         PhiMmaMaps mm;
-        const bool mma = phi_mma_eligible(n, D);
-        if (mma) TRY(fill_mma_maps(mm, kf, kz, p->Dth ? kt : nullptr, n, n, xs, gs, D));
+        if (mma) TRY(fill_mma_maps(mm, ksp, p->Dth > 0, n, n, xs, gs, D));
         TRY(launch_phi(p, q, stream, mma ? &mm : nullptr));
         CU(cudaMemcpy2DAsync(phi_z, fz, phi, fd, fz, n, cudaMemcpyDeviceToDevice, stream));
         if (phi_th && p->Dth) CU(cudaMemcpy2DAsync(phi_th, ft, phi + p->Dz, fd, ft, n, cudaMemcpyDeviceToDevice, stream));

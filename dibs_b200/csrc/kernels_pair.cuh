@@ -33,6 +33,10 @@ struct PairParams {
     uint32_t* phi_cnt;                   // [row tiles][column tiles] arrival counters of the phi pass
     PeerWait wait_x, wait_g;             // peer-memory exchange: flags to wait on before reading x_all / g_all
     float* kz; float* kt; float* kfull;  // [n_rows][n_all]
+    // tensor-core phi: the same three planes split into TF32 hi / lo parts by the kernel that produces them, so the
+    // phi kernel's TMA loads are MMA operands as they land ([6][n_rows][n_all]: K hi, K lo, K_z hi, K_z lo, K_t hi,
+    // K_t lo; null: not needed)
+    float* k_split;
     float h_z, h_t, scale_z, scale_t;
     // epilogue of the phi pass (optimizer step; svgd.py:265,718-719)
     float* x_next; int next_ld;          // updated rows of this rank (null: phi only)
@@ -142,7 +146,17 @@ __global__ void __launch_bounds__(256) k_pair_finish(PairParams p) {
         float kt = p.dth > 0 ? p.scale_t * expf(-dt / p.h_t) : 0.0f;
         p.kz[e] = kz;
         if (p.kt) p.kt[e] = kt;
-        p.kfull[e] = kz + kt;
+        const float kf = kz + kt;
+        p.kfull[e] = kf;
+        if (p.k_split) {
+            // x = hi + lo exactly, hi = x rounded to the nearest TF32 value (kernels_phi_mma.cuh)
+            const float fh = __uint_as_float((__float_as_uint(kf) + 0x1000u) & 0xFFFFE000u);
+            const float zh = __uint_as_float((__float_as_uint(kz) + 0x1000u) & 0xFFFFE000u);
+            const float th = __uint_as_float((__float_as_uint(kt) + 0x1000u) & 0xFFFFE000u);
+            p.k_split[e] = fh; p.k_split[plane + e] = kf - fh;
+            p.k_split[2 * plane + e] = zh; p.k_split[3 * plane + e] = kz - zh;
+            if (p.kt) { p.k_split[4 * plane + e] = th; p.k_split[5 * plane + e] = kt - th; }
+        }
     }
 }
 

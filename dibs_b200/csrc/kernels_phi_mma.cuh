@@ -17,8 +17,8 @@
 // the j slices are those of the SIMT kernel (fixed length on the GLOBAL particle index), partial tiles go to the same
 // phi_part planes and the same last-arriver epilogue sums them in fixed order and applies the optimizer step.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation), warps 2-5 = operand
-// splitters during the main loop (thread = row of the A tiles; they also accumulate rowsum(K*) in fp32) and the
-// epilogue afterwards (thread = TMEM lane = row).
+// splitters during the main loop (hi / lo parts of the G and X tiles; thread = row of the K* tile for rowsum(K*) in
+// fp32; the K planes arrive already split from k_pair_finish) and the epilogue afterwards (thread = TMEM lane = row).
 //
 // Shared-memory operand layouts are the canonical 128-byte-swizzled ones a plain 2-D TMA box produces:
 //   A = K tiles, K-major:   [128 rows][32 j] fp32, rows of 128 B, 16-byte chunks XOR-swizzled by (row & 7);
@@ -48,7 +48,7 @@ constexpr int MM_SMEM_BYTES = MM_STAGES * MM_STAGE_BYTES + 1024 /*alignment*/ + 
 constexpr int MM_TMEM_COLS = 128;                     // D1 (drive) 64 columns + D2 (K* X) 64 columns
 
 struct PhiMmaMaps {
-    CUtensorMap a_full, a_z, a_t;     // K, K_z, K_theta  [n_rows][n_all]
+    CUtensorMap a[6];                 // K hi, K lo, K_z hi, K_z lo, K_theta hi, K_theta lo  [n_rows][n_all] (PairParams::k_split)
     CUtensorMap b_x, b_g;             // particles / gradients [n_all][ld]
 };
 
@@ -161,10 +161,14 @@ k_phi_mma(const __grid_constant__ PairParams p, const __grid_constant__ PhiMmaMa
     const int j_end = min(p.n_all, j_begin + p.j_len);
     const int n_it = (j_end - j_begin + MM_KS - 1) / MM_KS;
     const bool same_a = (p.dth == 0);                // marginal: K* == K, one A tile feeds both products
-    const CUtensorMap* map_a2 = z_block ? &maps.a_z : &maps.a_t;
+    const CUtensorMap* map_a2 = z_block ? &maps.a[2] : &maps.a[4];        // K* hi (lo = the next map)
     const float h = z_block ? p.h_z : p.h_t;
 
     if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.a[0])) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map_a2)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.b_g)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.b_x)) : "memory");
         for (int s = 0; s < MM_STAGES; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_split + s, 4); mbar_init(bar_empty + s, 1); }
         mbar_init(bar_accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -188,14 +192,18 @@ k_phi_mma(const __grid_constant__ PairParams p, const __grid_constant__ PhiMmaMa
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            const uint32_t bytes = (same_a ? 1 : 2) * MM_A_BYTES + 2 * MM_B_BYTES;
+            const uint32_t bytes = (same_a ? 2 : 4) * MM_A_BYTES + 2 * MM_B_BYTES;
             for (int it = 0; it < n_it; ++it) {
                 const int s = it % MM_STAGES;
                 if (it >= MM_STAGES) mbar_wait(bar_empty + s, ((it / MM_STAGES) - 1) & 1);
                 const int j0 = j_begin + it * MM_KS;
                 mbar_expect_tx(bar_full + s, bytes);
-                tma_load_2d(stage_ptr(s, 0), &maps.a_full, bar_full + s, j0, i0);
-                if (!same_a) tma_load_2d(stage_ptr(s, 2), map_a2, bar_full + s, j0, i0);
+                tma_load_2d(stage_ptr(s, 0), &maps.a[0], bar_full + s, j0, i0);
+                tma_load_2d(stage_ptr(s, 1), &maps.a[1], bar_full + s, j0, i0);
+                if (!same_a) {
+                    tma_load_2d(stage_ptr(s, 2), map_a2, bar_full + s, j0, i0);
+                    tma_load_2d(stage_ptr(s, 3), map_a2 + 1, bar_full + s, j0, i0);
+                }
                 tma_load_2d(stage_ptr(s, 4), &maps.b_g, bar_full + s, c0, j0);
                 tma_load_2d(stage_ptr(s, 4) + MM_B_BYTES / 2, &maps.b_g, bar_full + s, c0 + 32, j0);
                 tma_load_2d(stage_ptr(s, 6), &maps.b_x, bar_full + s, c0, j0);
@@ -244,18 +252,16 @@ k_phi_mma(const __grid_constant__ PairParams p, const __grid_constant__ PhiMmaMa
         for (int it = 0; it < n_it; ++it) {
             const int s = it % MM_STAGES;
             mbar_wait(bar_full + s, (it / MM_STAGES) & 1);
-            // A tiles: this thread's row, 8 chunks of 16 B; logical chunk c sits at position c ^ (row & 7)
-            for (int a = 0; a < (same_a ? 1 : 2); ++a) {
-                float4* hi = reinterpret_cast<float4*>(stage_ptr(s, 2 * a)) + row * 8;
-                float4* lo = reinterpret_cast<float4*>(stage_ptr(s, 2 * a + 1)) + row * 8;
+            // K* tile (already split by the kernel that produced K): this thread's row of hi + lo, 8 chunks of 16 B each
+            // -- logical chunk c sits at position c ^ (row & 7) -- summed in j order into the row sum
+            {
+                const float4* hi = reinterpret_cast<const float4*>(stage_ptr(s, same_a ? 0 : 2)) + row * 8;
+                const float4* lo = reinterpret_cast<const float4*>(stage_ptr(s, same_a ? 1 : 3)) + row * 8;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const int pos = c ^ (row & 7);
-                    const float4 v = hi[pos];
-                    if (a == (same_a ? 0 : 1)) rs += (v.x + v.y) + (v.z + v.w);
-                    float4 h4, l4;
-                    split_tf32(v, h4, l4);
-                    hi[pos] = h4; lo[pos] = l4;
+                    const float4 vh = hi[pos], vl = lo[pos];
+                    rs += ((vh.x + vl.x) + (vh.y + vl.y)) + ((vh.z + vl.z) + (vh.w + vl.w));
                 }
             }
             // B tiles: 2 tiles x 512 chunks, elementwise (the swizzle is the same permutation in hi and lo)

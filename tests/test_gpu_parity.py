@@ -290,7 +290,8 @@ def test_step_vs_oracle_n_vars_20(lik, d, m, s):
         assert err <= 4 * gap + 2e-5 * scale + 1e-6, (which, err, gap, scale)
 
 
-@pytest.mark.parametrize("lik,d,m,s", [c for c in VARIANT_CASES if c[1] > 20])
+# + two cases with >= 512 particles: the step loop then runs phi on the tensor cores (kernels_phi_mma.cuh)
+@pytest.mark.parametrize("lik,d,m,s", [c for c in VARIANT_CASES if c[1] > 20] + [("lingauss", 8, 512, 4), ("bge", 8, 512, 4)])
 def test_two_steps_vs_oracle_large_n_vars(lik, d, m, s):
     """Two whole ``_svgd_step``s through ``dibs_svgd_steps`` (CUDA-graph path: MC passes, acyclicity, kernel matrix,
     phi, optimizer of the n_vars > 20 kernel variants together) against the oracle on the same seeded inputs.

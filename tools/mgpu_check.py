@@ -14,8 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.environ.get("MGPU_OUT") or os.path.join(ROOT, "gpurun_out")
 CASES = {"lin": dict(d=20, m=64, s=32, steps=7), "bge": dict(d=12, m=32, s=16, steps=5), "nn": dict(d=10, m=16, s=8, steps=4),
-         # >= 128 particles: the tensor-core phi kernel (its choice depends on the GLOBAL particle count only)
-         "linL": dict(d=12, m=256, s=8, steps=3)}
+         # >= 512 particles: the tensor-core phi kernel (its choice depends on the GLOBAL particle count only)
+         "linL": dict(d=12, m=512, s=8, steps=3)}
 
 
 def run():
