@@ -262,9 +262,11 @@ static McShape mc_shape_for(bool qr, int likelihood, int d, int hidden, int n_lo
         sh.gpb = best;
         sh.threads = ((best * d) + 31) / 32 * 32;
         const int rounds = ceil_div(Q, best);
-        // up to 8 chunks per particle whatever the number of particles a rank owns: the chunking fixes the order in which
-        // the online-softmax partials are merged, so it must not depend on the rank count (bit-identical results)
-        int chunks = 8;
+        // up to 4 chunks per particle whatever the number of particles a rank owns: the chunking fixes the order in which
+        // the online-softmax partials are merged, so it must not depend on the rank count (bit-identical results).
+        // 4 x 128 particles x 2 passes + the acyclicity CTAs still oversubscribe 148 SMs on 8 GPUs; 8 chunks cost 4 %
+        // of the step on one GPU (measured) for nothing
+        int chunks = 4;
         (void)n_local;
         if (chunks > rounds) chunks = rounds;
         if (chunks < 1) chunks = 1;
@@ -430,10 +432,13 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
         p->j_len = ceil_div(ceil_div(p->M, ns), PT_J) * PT_J;
         p->n_jsplit = ceil_div(p->M, p->j_len);
         // tensor-core phi (>= MMA_MIN_PARTICLES particles, see phi_mma_eligible): a CTA pays a fixed pipeline fill /
-        // TMEM / epilogue cost, so slices are long -- 512 particles, again a function of M only
+        // TMEM / epilogue cost (~5 us, then ~2.8 us per 32 particles: the kernel is bound by the L2 -> SM traffic of
+        // its operand tiles), so slices are longer than the SIMT kernel's -- 256 particles, again a function of M only:
+        // 8 stages per CTA, and still 80 CTAs when 8 ranks own 128 rows each (512-particle slices: 152 us on one GPU
+        // but only 40 CTAs, 78 us, on 8)
         const int ld_rows = (p->D + 3) & ~3;
         if (phi_mma_eligible(p->M, ld_rows, 512)) {
-            p->j_len = 512;
+            p->j_len = 256;
             p->n_jsplit = ceil_div(p->M, p->j_len);
         }
     }

@@ -46,7 +46,13 @@ __device__ __forceinline__ float entry_from_bits(uint32_t bits, float sa, bool f
     if (HARD) return bits_to_unit(bits) < sa ? 1.0f : 0.0f;
     const float u = logistic_u_from_bits(bits);
     // sigmoid(log(u/(1-u)) + a) = u / (u + (1-u) e^{-a}): the logistic noise and the sigmoid cancel analytically
-    if (fast_soft) return __fdividef(u, fmaf(1.0f - u, sa, u));
+    // u / (u + (1-u) e^{-a}) with the approximate reciprocal (1 ulp): one MUFU + one multiply; an infinite
+    // denominator (e^{-a} overflowed) gives 0, as the division would
+    if (fast_soft) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(1.0f - u, sa, u)));
+        return u * r;
+    }
     return sigmoidf_ref(tau * ((logf(u) - log1pf(-u)) + sa));
 }
 
@@ -54,8 +60,9 @@ __device__ __forceinline__ float entry_from_bits(uint32_t bits, float sa, bool f
 // column); a slot stride congruent to d (mod 32) makes the bank of such an access equal to the flat thread index
 __host__ __device__ inline int qr_pad_stride(int base, int d) { return base + ((d - base) % 32 + 32) % 32; }
 
-template <int DMAX, int MODE>
-__global__ void __launch_bounds__(192, (DMAX <= 20 ? 3 : 1))
+// FULL: n_vars == DMAX, the variable count is a compile-time constant (no padding rows: every `i < d` folds away)
+template <int DMAX, int MODE, bool FULL>
+__global__ void __launch_bounds__((DMAX <= 20 && MODE == MC_THETA_HARD ? 256 : 192), (DMAX <= 20 ? 2 : 1))
 k_mc_lin_qr(const __grid_constant__ McParams p, const __grid_constant__ RTri<DMAX> R) {
     extern __shared__ __align__(16) float smem[];
     constexpr bool HARD = (MODE == MC_THETA_HARD || MODE == MC_Z_SCORE);
@@ -63,7 +70,7 @@ k_mc_lin_qr(const __grid_constant__ McParams p, const __grid_constant__ RTri<DMA
     constexpr int NS = DMAX + 1;                       // odd row stride of the node log-prob table
     constexpr int IL = 4;                              // independent threefry chains per thread
     static_assert(DMAX % IL == 0 && DMAX <= 32, "row batches of 4; one bit per row in the hard-graph masks");
-    const int d = p.d, dd = d * d, gpb = p.gpb;        // gpb = sample pairs ("slots") per round, <= 16
+    const int d = FULL ? DMAX : p.d, dd = d * d, gpb = p.gpb;        // gpb = sample pairs ("slots") per round, <= 16
     const int m = blockIdx.x, c = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const int t = p.st ? p.st->t : p.t_override;
     const int S = p.n_samples, Qh = (S + 1) >> 1;      // slot q holds samples q and q + Qh
@@ -149,23 +156,25 @@ k_mc_lin_qr(const __grid_constant__ McParams p, const __grid_constant__ RTri<DMA
 #pragma unroll
             for (int w = 0; w < IL; ++w) {
                 const int i = i0 + w;
-                // zero_diagonal (utils/func.py:117-125): diagonal draws are consumed and discarded
-                const bool real = v0 && i < d && i != j;
-                float ga = 0.0f, gb = 0.0f;
-                if (real) {
-                    const float sa = sA[i * DMAX + j];
-                    if (use_ext) { ga = __uint_as_float(x0[w]); gb = __uint_as_float(x1[w]); }
-                    else {
-                        ga = entry_from_bits<HARD>(x0[w], sa, fast_soft, p.tau);
-                        gb = v1 ? entry_from_bits<HARD>(x1[w], sa, fast_soft, p.tau) : 0.0f;
-                    }
-                    // log p(theta | G): sum g * logN(theta; mean_edge, sig_edge)   (linearGaussian.py:289)
-                    const float lpth = sLpTh[i * DMAX + j];
-                    prior0 = fmaf(ga, lpth, prior0);
-                    prior1 = fmaf(gb, lpth, prior1);
+                // zero_diagonal (utils/func.py:117-125): diagonal draws are consumed and discarded.  Branch-free: the
+                // entries of padding rows, of the diagonal and of slots past the chunk are computed and then zeroed
+                const bool real = v0 && (FULL || i < d) && i != j;
+                const bool in_tab = FULL || i < d;
+                const float sa = in_tab ? sA[i * DMAX + j] : 0.0f;
+                // log p(theta | G): sum g * logN(theta; mean_edge, sig_edge)   (linearGaussian.py:289)
+                const float lpth = in_tab ? sLpTh[i * DMAX + j] : 0.0f;
+                float ga, gb;
+                if (use_ext) { ga = __uint_as_float(x0[w]); gb = __uint_as_float(x1[w]); }
+                else {
+                    ga = entry_from_bits<HARD>(x0[w], sa, fast_soft, p.tau);
+                    gb = entry_from_bits<HARD>(x1[w], sa, fast_soft, p.tau);
                 }
+                ga = real ? ga : 0.0f;
+                gb = (real && v1) ? gb : 0.0f;
+                prior0 = fmaf(ga, lpth, prior0);
+                prior1 = fmaf(gb, lpth, prior1);
                 if (HARD && !use_ext) { gm0 |= (ga != 0.0f ? 1u : 0u) << i; gm1 |= (gb != 0.0f ? 1u : 0u) << i; }
-                else if (active && i < d) { sG[i * DMAX] = ga; sG[MAT + i * DMAX] = gb; }     // own column only
+                else if (active && (FULL || i < d)) { sG[i * DMAX] = ga; sG[MAT + i * DMAX] = gb; }     // own column only
             }
         }
         float* sNd = sNode + buf * (2 * gpb * NS);
@@ -179,7 +188,7 @@ k_mc_lin_qr(const __grid_constant__ McParams p, const __grid_constant__ RTri<DMA
 #pragma unroll
             for (int i = 0; i < DMAX; ++i) {
                 float gv = 0.0f, th = 0.0f;
-                if (i < d) {
+                if (FULL || i < d) {
                     gv = (HARD && !use_ext) ? (((gm >> i) & 1u) ? 1.0f : 0.0f) : sGg[i * DMAX];
                     th = sTh[i * DMAX + j];
                 }
@@ -215,7 +224,7 @@ k_mc_lin_qr(const __grid_constant__ McParams p, const __grid_constant__ RTri<DMA
             if (MODE != MC_LP_ONLY) {
 #pragma unroll
                 for (int i = 0; i < DMAX; ++i) {
-                    if (i < d) {
+                    if (FULL || i < d) {
                         float val;
                         if (MODE == MC_THETA_HARD) {
                             // d/dtheta: g * (-(theta-mu)/sig^2) + g * (x^T R)/s2          
@@ -263,7 +272,7 @@ k_mc_lin_qr(const __grid_constant__ McParams p, const __grid_constant__ RTri<DMA
             if (active) {
 #pragma unroll
                 for (int i = 0; i < DMAX; ++i)
-                    if (i < d) sAcc[i * DMAX] = fmaf(sAcc[i * DMAX], scale, fmaf(e0, sG[i * DMAX], e1 * sG[MAT + i * DMAX]));
+                    if (FULL || i < d) sAcc[i * DMAX] = fmaf(sAcc[i * DMAX], scale, fmaf(e0, sG[i * DMAX], e1 * sG[MAT + i * DMAX]));
             }
         }
         // no second barrier: the next round writes the OTHER node buffer and only private columns

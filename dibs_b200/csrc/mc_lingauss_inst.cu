@@ -24,7 +24,7 @@ int DIBS_CAT(launch_mc_linqr_, DIBS_DMAX)(int mode, const McParams& q, dim3 grid
     for (int i = 0; i < DIBS_DMAX * (DIBS_DMAX + 1) / 2; ++i) R.v[i] = r_packed_host[i];
 #define DIBS_GO(M)                                                                                          \
     {                                                                                                       \
-        auto kern = k_mc_lin_qr<DIBS_DMAX, M>;                                                              \
+        auto kern = (q.d == DIBS_DMAX) ? k_mc_lin_qr<DIBS_DMAX, M, true> : k_mc_lin_qr<DIBS_DMAX, M, false>; \
         if (smem > 48 * 1024) {                                                                             \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return (int)e;                                                            \
