@@ -16,6 +16,7 @@
 #include "kernels_mc.cuh"
 #include "kernels_mc_lin_qr.cuh"
 #include "kernels_mc_bge.cuh"
+#include "kernels_mc_bge_soft.cuh"
 #include "bge_prepare.cuh"
 #include "kernels_mc_nn.cuh"
 #include "kernels_prior.cuh"
@@ -350,8 +351,8 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
         return fail(DIBS_ERR_INVALID_ARG, "n_particles must be divisible by world_size and 0 <= rank < world_size");
     if (c.joint && c.likelihood == DIBS_LIK_BGE) return fail(DIBS_ERR_INVALID_ARG, "BGe is a marginal likelihood: use MarginalDiBS");
     if (!c.joint && c.likelihood != DIBS_LIK_BGE) return fail(DIBS_ERR_UNSUPPORTED, "MarginalDiBS is implemented for BGe only");
-    if (c.likelihood == DIBS_LIK_BGE && c.grad_estimator_z != DIBS_ESTIMATOR_SCORE)
-        return fail(DIBS_ERR_UNSUPPORTED, "BGe + reparam estimator is not implemented natively (SURVEY 8f rank 3)");
+    if (c.likelihood == DIBS_LIK_BGE && c.grad_estimator_z != DIBS_ESTIMATOR_SCORE && c.n_vars > 32)
+        return fail(DIBS_ERR_UNSUPPORTED, "BGe + reparam estimator (soft-graph BGe) is implemented for n_vars <= 32");
     if (c.likelihood < 0 || c.likelihood > 2) return fail(DIBS_ERR_UNSUPPORTED, "unknown likelihood model");
     if (c.likelihood == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN && (c.hidden < 1 || c.hidden > 32))
         return fail(DIBS_ERR_UNSUPPORTED, "DenseNonlinearGaussian: one hidden layer of 1..32 units is implemented");
@@ -683,7 +684,8 @@ extern "C" int dibs_set_data(dibs_plan* p, const float* x, const int32_t* mask, 
 static McShape mc_shape(const dibs_plan* p, int n_local, int S, bool lp_only) {
     if (p->use_dense) return mc_shape_dense(p->d, n_local, S, !lp_only && !p->cfg.prng_partitionable);
     const bool qr = p->use_qr && (lp_only || (!p->cfg.prng_partitionable && (S % 2) == 0));
-    return mc_shape_for(qr, p->cfg.likelihood, p->d, p->cfg.hidden, n_local, S, !lp_only && !p->cfg.prng_partitionable);
+    const bool bge_soft = p->cfg.likelihood == DIBS_LIK_BGE && p->cfg.grad_estimator_z == DIBS_ESTIMATOR_REPARAM;
+    return mc_shape_for(qr, p->cfg.likelihood, p->d, p->cfg.hidden, n_local, S, !lp_only && !p->cfg.prng_partitionable && !bge_soft);
 }
 static void apply_shape(McParams& q, const McShape& sh) {
     q.n_chunks = sh.chunks; q.s_per_chunk = sh.spc; q.gpb = sh.gpb; q.paired = sh.paired ? 1 : 0;
@@ -719,6 +721,7 @@ static void fill_mc(const dibs_plan* p, const Src& s, McParams& q) {
     }
     q.hidden = p->cfg.hidden; q.hp = nn_hp(p->cfg.hidden);
     q.bge_r = p->bge_r; q.bge_r_stride = p->bge_r_stride; q.bge_table = p->bge_table; q.bge_coef = p->bge_coef;
+    q.bge_alpha_mu = p->cfg.bge_alpha_mu; q.bge_alpha_lambd = p->cfg.bge_alpha_lambd;
 }
 
 template <typename K>
@@ -734,6 +737,10 @@ DECL_MC(nn, 8) DECL_MC(nn, 16) DECL_MC(nn, 20) DECL_MC(nn, 32) DECL_MC(nn, 64) D
 DECL_MC(bge, 8) DECL_MC(bge, 16) DECL_MC(bge, 20) DECL_MC(bge, 32) DECL_MC(bge, 64)
 #undef DECL_MC
 namespace dibs {
+int launch_mc_bgesoft_8(int, const McParams&, dim3, size_t, cudaStream_t);
+int launch_mc_bgesoft_16(int, const McParams&, dim3, size_t, cudaStream_t);
+int launch_mc_bgesoft_20(int, const McParams&, dim3, size_t, cudaStream_t);
+int launch_mc_bgesoft_32(int, const McParams&, dim3, size_t, cudaStream_t);
 int launch_mc_linqr_8(int, const McParams&, dim3, int, size_t, const float*, cudaStream_t);
 int launch_mc_linqr_16(int, const McParams&, dim3, int, size_t, const float*, cudaStream_t);
 int launch_mc_linqr_20(int, const McParams&, dim3, int, size_t, const float*, cudaStream_t);
@@ -767,6 +774,22 @@ static int launch_mc(const dibs_plan* p, McParams q, const McShape& sh, cudaStre
             case 16: e = launch_mc_linqr_16(MODE, q, grid, sh.threads, smem, p->lin_r.data(), stream); break;
             case 20: e = launch_mc_linqr_20(MODE, q, grid, sh.threads, smem, p->lin_r.data(), stream); break;
             default: e = launch_mc_linqr_32(MODE, q, grid, sh.threads, smem, p->lin_r.data(), stream); break;
+        }
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (e != 0) return fail(DIBS_ERR_CUDA, std::string("MC kernel launch: ") + cudaGetErrorString((cudaError_t)e));
+        return DIBS_OK;
+    }
+    if (lik == DIBS_LIK_BGE && p->cfg.grad_estimator_z == DIBS_ESTIMATOR_REPARAM) {
+        // soft-graph BGe: one kernel for the reparameterisation pass and for log-probs of supplied (soft or hard) graphs
+        if (MODE != MC_Z_REPARAM && MODE != MC_LP_ONLY) return fail(DIBS_ERR_STATE, "BGe + reparam plan asked for a hard-graph pass");
+        q.paired = 0;
+        smem = std::max(mc_bge_soft_smem(p->d, p->dmax, p->bge_r_stride == 0), fuse_smem);
+        if (smem > 227 * 1024) return fail(DIBS_ERR_UNSUPPORTED, "problem size needs more than 227 KB of shared memory per CTA");
+        switch (p->dmax) {
+            case 8: e = launch_mc_bgesoft_8(MODE, q, grid, smem, stream); break;
+            case 16: e = launch_mc_bgesoft_16(MODE, q, grid, smem, stream); break;
+            case 20: e = launch_mc_bgesoft_20(MODE, q, grid, smem, stream); break;
+            default: e = launch_mc_bgesoft_32(MODE, q, grid, smem, stream); break;
         }
         g_launches.fetch_add(1, std::memory_order_relaxed);
         if (e != 0) return fail(DIBS_ERR_CUDA, std::string("MC kernel launch: ") + cudaGetErrorString((cudaError_t)e));

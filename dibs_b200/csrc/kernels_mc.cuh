@@ -40,6 +40,7 @@ struct McParams {
     int bge_r_stride;                    // d*d if per-node R (interventions), 0 if shared
     const float* bge_table;              // [d][d+1]: log-gamma terms for (node j, n_parents l)
     const float* bge_coef;               // [d][2]: (N_j + alpha_lambd - d), valid flag
+    float bge_alpha_mu, bge_alpha_lambd; // hyper-parameters (soft-graph BGe: log-gamma terms at real-valued parent counts)
     const float* g_ext;                  // [n_local, S, d, d] graphs supplied by the caller (hooks) or null
     float* part_acc; int acc_size;       // [n_local][n_chunks][acc_size]
     float* part_stats;                   // [n_local][n_chunks][4]: running max, sum exp, sum lp, -

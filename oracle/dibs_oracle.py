@@ -348,6 +348,58 @@ def bge_logmarginal(g, x, mask, lik, dt, pre=None):
     return total.astype(dt)
 
 
+def bge_logmarginal_grads(g, x, mask, lik, dt, pre=None):
+    """BGe score and its gradient w.r.t. a SOFT graph g[S,d,d] (the 'reparam' estimator with BGe, README.md:88-90;
+    linearGaussian.py:82-118 with real-valued ``n_parents``; _slogdet_jax, utils/func.py:128-145).
+
+    Per node j with p = g[:, j] (p_j = 0), l = sum p, A = D R D + I - D^2 (D = diag p), u_a = p_a R_aj:
+      logdet B = logdet A + log s,  s = R_jj - u^T A^-1 u        (B = the same with q = p + e_j)
+      d logdet A / dp_i = 2 sum_b (A^-1)_ib p_b (R_ib - delta_ib)
+      d s / dp_i        = -2 R_ij w_i + 2 w_i sum_b p_b (R_ib - delta_ib) w_b,   w = A^-1 u
+    and the log-gamma terms differentiate through l with digamma.  Returns (lp[S], dlp/dg[S,d,d]).
+    """
+    from scipy.special import digamma
+    s_n, d, _ = g.shape
+    r_all, n_all, small_t, alpha_mu, alpha_lambd = pre if pre is not None else bge_precompute(x, mask, lik, dt)
+    g = g.astype(dt)
+    eye = np.eye(d, dtype=dt)
+    lp = np.zeros(s_n, dt)
+    dg = np.zeros((s_n, d, d), dt)
+    for j in range(d):
+        n_j = n_all[j]
+        if np.isclose(n_j, 0):
+            continue
+        r = r_all[j].astype(dt)
+        for si in range(s_n):
+            p = g[si, :, j].copy()
+            p[j] = 0
+            l = p.sum()
+            a = (p[:, None] * p[None, :]) * r + (1 - p[:, None] * p[None, :]) * eye
+            ainv = np.linalg.inv(a)
+            la = np.linalg.slogdet(a)[1]
+            u = p * r[:, j]
+            w = ainv @ u
+            sch = r[j, j] - u @ w
+            lb = la + np.log(sch)
+            c1 = dt(0.5) * (n_j + alpha_lambd - d + l)
+            c2 = dt(0.5) * (n_j + alpha_lambd - d + l + 1)
+            log_gamma = (dt(0.5) * (np.log(alpha_mu) - np.log(n_j + alpha_mu))
+                         + gammaln(dt(0.5) * (n_j + alpha_lambd - d + l + 1)) - gammaln(dt(0.5) * (alpha_lambd - d + l + 1))
+                         - dt(0.5) * n_j * np.log(dt(np.pi)) + dt(0.5) * (alpha_lambd - d + 2 * l + 1) * np.log(small_t))
+            lp[si] += log_gamma + c1 * la - c2 * lb
+            rm = r - eye
+            dla = 2 * ((ainv * rm) @ p)
+            t = rm @ (p * w)
+            dsch = -2 * r[:, j] * w + 2 * w * t
+            dlb = dla + dsch / sch
+            dlg = (dt(0.5) * digamma(dt(0.5) * (n_j + alpha_lambd - d + l + 1)) - dt(0.5) * digamma(dt(0.5) * (alpha_lambd - d + l + 1))
+                   + np.log(small_t))
+            col = dlg + dt(0.5) * la - dt(0.5) * lb + c1 * dla - c2 * dlb
+            col[j] = 0
+            dg[si, :, j] = col
+    return lp.astype(dt), dg.astype(dt)
+
+
 def log_joint(cfg, g, theta, x, mask, dt, want_grads=True, pre=None):
     k = cfg.lik.kind
     if k == "lingauss":
@@ -355,6 +407,9 @@ def log_joint(cfg, g, theta, x, mask, dt, want_grads=True, pre=None):
     if k == "densenn":
         return densenn_logjoint(g, theta, x, mask, cfg.lik, dt, want_grads)
     if k == "bge":
+        if want_grads and cfg.grad_estimator_z == "reparam":
+            lp, dg = bge_logmarginal_grads(g, x, mask, cfg.lik, dt, pre)
+            return lp, dg, None
         return bge_logmarginal(g, x, mask, cfg.lik, dt, pre), None, None
     raise NotImplementedError(k)
 

@@ -135,7 +135,7 @@ def make_case(name, *, lik, prior="er", epn=1, d=5, n_obs=20, m=3, s=8, a=4, t=7
     out["soft_g"] = npy(soft)
     th_i = (lambda i: None) if not joint else (lambda i: jax.tree_util.tree_map(lambda l: l[i], theta))
     out["logprob_hard"] = npy(torch.stack([model.eltwise_log_joint_prob(gs[i], th_i(i), None) for i in range(m)]))
-    if joint:
+    if joint or estimator == "reparam":
         out["logprob_soft"] = npy(torch.stack([model.eltwise_log_joint_prob(soft[i], th_i(i), None) for i in range(m)]))
     out["acyclic_h_hard"] = npy(torch.stack([acyclic_constr_nograd(gs[i, 0], d) for i in range(m)]))
     out["acyclic_h_soft"] = npy(torch.stack([acyclic_constr_nograd(soft[i, 0], d) for i in range(m)]))
@@ -246,6 +246,11 @@ if __name__ == "__main__":
               optimizer="gd", seed=2, n_dim=4, tau=0.7, beta_linear=0.5)
     make_case("step_joint_lingauss_score", lik="lingauss", prior="uniform", d=4, m=3, s=8, a=4, t=5,
               estimator="score", baseline=0.05, seed=3)
+    # BGe with the reparameterisation estimator (soft graphs, real-valued parent counts)
+    make_case("step_marginal_bge_reparam", lik="bge", prior="er", epn=1, d=6, m=3, s=8, a=4, t=4, estimator="reparam",
+              seed=6, alpha_linear=0.25)
+    make_case("step_marginal_bge_reparam_interv", lik="bge", prior="sf", d=5, m=3, s=6, a=4, t=3, estimator="reparam",
+              interv=True, seed=7, alpha_linear=0.3)
     make_case("step_joint_densenn_er", lik="densenn", prior="er", epn=1, d=5, m=3, s=8, a=4, t=6, hidden=4, seed=4)
     make_case("step_joint_densenn_sf_interv", lik="densenn", prior="sf", d=6, m=3, s=7, a=3, t=9, hidden=5, interv=True, seed=5)
     # BASELINE.json configs[0]: MarginalDiBS BGe n_vars=5 n_particles=4 steps=50 (sf prior because ER p>=1 at d=5)

@@ -10,6 +10,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 STEP_CASES = [
     "step_marginal_bge_sf",
     "step_marginal_bge_er_interv_baseline",
+    "step_marginal_bge_reparam",
+    "step_marginal_bge_reparam_interv",
     "step_joint_lingauss_er",
     "step_joint_lingauss_sf_interv_gd",
     "step_joint_lingauss_score",
