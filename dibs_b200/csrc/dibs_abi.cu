@@ -220,7 +220,7 @@ static int pick_dmax(int d) {
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // CTAs per particle of the acyclicity pass (a function of (A, d, PRNG layout) only)
-constexpr int ACYC_WPC = 4;      // warps (= sample pairs) per CTA of the row-per-lane kernel
+constexpr int ACYC_WPC = ACYC_SLOTS / 2;      // sample pairs per CTA of the row-per-thread kernel
 
 static int mc_target_ctas(int per_sm) { return per_sm * 148; }
 static bool acyc_rows_path(const dibs_plan* p) {
@@ -836,11 +836,10 @@ static int launch_acyc(const dibs_plan* p, const Src& s, int which_split, float*
     const size_t fuse_smem = fuse ? assemble_smem(p->d, p->k, fuse->a.z_chunks, fuse->a.th_chunks) : 0;
     const int d = p->d;
     if (acyc_rows_path(p)) {
-        // row-per-lane kernel: a warp per sample pair (both lanes of each threefry block are used)
-        const int warps = ACYC_WPC;
-        const size_t smem = std::max(acyclic_rows_smem(d, p->k, p->dmax, warps), fuse_smem);
+        // row-per-thread kernel: 4 sample pairs per CTA (both lanes of each threefry block are used)
+        const size_t smem = std::max(acyclic_rows_smem(d, p->dmax), fuse_smem);
         dim3 grid(s.n, acyc_chunks(p));
-#define ACYC_GO(DM) { TRY(set_smem(k_acyclic_rows<DM>, smem)); k_acyclic_rows<DM><<<grid, warps * 32, smem, stream>>>(a); }
+#define ACYC_GO(DM) { TRY(set_smem(k_acyclic_rows<DM>, smem)); k_acyclic_rows<DM><<<grid, acyclic_rows_threads(d), smem, stream>>>(a); }
         switch (p->dmax) {
             case 8: ACYC_GO(8) break;
             case 16: ACYC_GO(16) break;
