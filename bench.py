@@ -1,25 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- SVGD steps/sec of the DiBS particle-update hot path on B200 (driver contract: see DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl native|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload t_lin] [--impl native|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
 One "step" = one full ``_svgd_step`` (reference: dibs/inference/svgd.py:226-267 / 673-721) over ALL particles of the
-workload; the metric is SVGD steps/sec (BASELINE.json).  N > 1 shards the particles of the SAME workload over the
-ranks (one all-gather per step), i.e. strong scaling.  Rank 0 prints ONE JSON line.
+workload; the metric is SVGD steps/sec (BASELINE.json).  Default workload: the north-star target shape, JointDiBS
+LinearGaussian n_vars=20 n_particles=1024 n_mc=128 (`t_lin`); the other single-GPU configs of BASELINE.json ride in the
+same JSON line as short runs (`also`).  N > 1 shards the particles of the SAME workload over the ranks (strong scaling).
+Rank 0 prints ONE JSON line.
 
 native arm
   value      K steps, state resident in HBM, every step bracketed by CUDA events on the launching stream with a
              256 MiB memset (> 126 MB L2) before each step outside the bracket (cold L2); max over ranks.
   e2e        the same metric through the public API with HOST buffers: ``JointDiBS(x=<pinned host array>, ...)
              .sample(key=, n_particles=, steps=K)`` and the returned particles copied back to host memory,
-             wall clock around the whole call (upload of x, plan creation, particle init, K steps, download).
+             wall clock around the whole call (upload of x, particle init, K steps, final Z -> G, download; the native
+             plan is cached per process, keyed on configuration + data digest, and was created by a warm-up call).
   roofline   dominant kernel of the step: per-kernel device time from events after every launch (eager replay of
-             the same kernels), algorithmic flops/bytes from DESIGN.md section 4.
+             the same kernels behind a delay kernel, so launch gaps are not charged), algorithmic flops/bytes from
+             DESIGN.md section 4; `passes` = the kernel-matrix and edge-probability passes the north star names,
+             against SURVEY 8(d)'s algorithmic bytes and flops; `traffic` = ncu DRAM bytes (profiles/traffic.json).
   cpu_baseline  the NumPy oracle (restated reference) on this box's host cores on a bounded sample of particles.
 reference arm (--impl reference): the oracle port of the reference's CPU path timed on the host cores (JAX is not
   installable in this image and the reference has no native sources, so there is no oracle/_ref build).
+DIBS_BENCH_TIMELINE=1 adds `timeline_end_us`: the step GRAPH replayed with an event node behind every kernel.
 """
 import argparse
 import json

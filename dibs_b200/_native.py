@@ -12,6 +12,7 @@ LIK = {"bge": 0, "lingauss": 1, "densenn": 2}
 PRIOR = {"er": 0, "sf": 1, "uniform": 2}
 ESTIMATOR = {"score": 0, "reparam": 1}
 OPTIMIZER = {"gd": 0, "rmsprop": 1}
+ACTIVATION = {"relu": 0, "tanh": 1, "sigmoid": 2, "leakyrelu": 3}
 PEER_MAX = 16          # ranks the peer-memory flag table holds (kernels_peer.cuh)
 
 
@@ -24,7 +25,7 @@ class DibsConfig(ctypes.Structure):
             "alpha_linear", "beta_linear", "tau", "score_function_baseline", "latent_prior_std",
             "h_latent", "h_theta", "scale_latent", "scale_theta", "stepsize", "er_p",
             "obs_noise", "mean_edge", "sig_edge", "min_edge", "sig_param", "bge_alpha_mu", "bge_alpha_lambd")] + [
-        ("world_size", ctypes.c_int32), ("rank", ctypes.c_int32)]
+        ("world_size", ctypes.c_int32), ("rank", ctypes.c_int32), ("activation", ctypes.c_int32)]
 
 
 _P = ctypes.c_void_p

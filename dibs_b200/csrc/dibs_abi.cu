@@ -354,6 +354,8 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
     if (c.likelihood == DIBS_LIK_BGE && c.grad_estimator_z != DIBS_ESTIMATOR_SCORE && c.n_vars > 32)
         return fail(DIBS_ERR_UNSUPPORTED, "BGe + reparam estimator (soft-graph BGe) is implemented for n_vars <= 32");
     if (c.likelihood < 0 || c.likelihood > 2) return fail(DIBS_ERR_UNSUPPORTED, "unknown likelihood model");
+    if (c.likelihood == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN && (c.activation < 0 || c.activation > 3))
+        return fail(DIBS_ERR_INVALID_ARG, "Invalid activation function");      /* KeyError in the reference (nonlinearGaussian.py:61) */
     if (c.likelihood == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN && (c.hidden < 1 || c.hidden > 32))
         return fail(DIBS_ERR_UNSUPPORTED, "DenseNonlinearGaussian: one hidden layer of 1..32 units is implemented");
     if (pick_dmax(c.n_vars) == 0) return fail(DIBS_ERR_UNSUPPORTED, "n_vars > 128 is not implemented");
@@ -719,7 +721,7 @@ static void fill_mc(const dibs_plan* p, const Src& s, McParams& q) {
     if (p->cfg.likelihood == DIBS_LIK_DENSE_NONLINEAR_GAUSSIAN) {
         q.mean_edge = 0.0f; q.sig2_edge = p->sig2_param; q.lognorm_edge = p->lognorm_param;
     }
-    q.hidden = p->cfg.hidden; q.hp = nn_hp(p->cfg.hidden);
+    q.hidden = p->cfg.hidden; q.hp = nn_hp(p->cfg.hidden); q.activation = p->cfg.activation;
     q.bge_r = p->bge_r; q.bge_r_stride = p->bge_r_stride; q.bge_table = p->bge_table; q.bge_coef = p->bge_coef;
     q.bge_alpha_mu = p->cfg.bge_alpha_mu; q.bge_alpha_lambd = p->cfg.bge_alpha_lambd;
 }
@@ -1024,6 +1026,19 @@ static int launch_phi(dibs_plan* p, const PairParams& q, cudaStream_t stream, co
     return DIBS_OK;
 }
 
+static int launch_edge_probs(dibs_plan* p, const float* z, int z_ld, int n, float alpha, float* p_out, int32_t* g_out, int raw,
+                             cudaStream_t stream) {
+    const int warps = edge_probs_warps(p->d, p->k);
+    const size_t smem = warps * edge_probs_smem_per_warp(p->d, p->k);
+    TRY(set_smem(k_edge_probs, smem));
+    int blocks = ceil_div(n, warps);
+    const int cap = 148 * 6;                      // grid-stride beyond ~6 CTAs per SM
+    if (blocks > cap) blocks = cap;
+    k_edge_probs<<<blocks, warps * 32, smem, stream>>>(z, z_ld, n, p->d, p->k, alpha, p_out, g_out, raw);
+    LAUNCHED();
+    return DIBS_OK;
+}
+
 // one full _svgd_step; reads the particles pk[cur], writes the updated local rows into pk[cur^1].
 // The raw scores / sub-keys of the step were produced by the previous step's k_opt_update (or by k_prologue
 // before the first step of a call); the loop state is read from st[cur] and carried into st[cur^1].
@@ -1101,7 +1116,7 @@ static int enqueue_step(dibs_plan* p, int cur, cudaStream_t stream, bool conc) {
     if (p->tl_capture >= 0) mark(p, stream, DIBS_PHASE_ASSEMBLE);     // timeline diagnostics: the join point before phi
     TRY(launch_phi(p, q, stream, p->phi_mma ? &p->mma_maps[cur] : nullptr));
     // raw scores U V^T of the NEXT step from the updated latent rows (edge-probability pass, dibs.py:179-181)
-    TRY(launch_prologue(p, q.x_next, p->ld, p->M_loc, p->row0, nullptr, nullptr, 0, 0u, p->scores, nullptr, stream));
+    TRY(launch_edge_probs(p, q.x_next, p->ld, p->M_loc, 0.0f, p->scores, nullptr, 1, stream));
     mark(p, stream, DIBS_PHASE_STEP_KEYS);
     return DIBS_OK;
 }
@@ -1419,26 +1434,14 @@ struct Scratch {
     }
 };
 
-static int launch_edge_probs(dibs_plan* p, const float* z, int n, float alpha, float* p_out, int32_t* g_out, cudaStream_t stream) {
-    const int warps = edge_probs_warps(p->d, p->k);
-    const size_t smem = warps * edge_probs_smem_per_warp(p->d, p->k);
-    TRY(set_smem(k_edge_probs, smem));
-    int blocks = ceil_div(n, warps);
-    const int cap = 148 * 6;                      // grid-stride beyond ~6 CTAs per SM
-    if (blocks > cap) blocks = cap;
-    k_edge_probs<<<blocks, warps * 32, smem, stream>>>(z, p->Dz, n, p->d, p->k, alpha, p_out, g_out);
-    LAUNCHED();
-    return DIBS_OK;
-}
-
 extern "C" int dibs_edge_probs(dibs_plan* p, const float* z, int32_t n, int32_t t, float* p_out, void* stream_) {
     if (!p || !z || !p_out || n < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_edge_probs: bad arguments");
-    return launch_edge_probs(p, z, n, p->cfg.alpha_linear * (float)t, p_out, nullptr, (cudaStream_t)stream_);
+    return launch_edge_probs(p, z, p->Dz, n, p->cfg.alpha_linear * (float)t, p_out, nullptr, 0, (cudaStream_t)stream_);
 }
 
 extern "C" int dibs_particle_to_g_lim(dibs_plan* p, const float* z, int32_t n, int32_t* g_out, void* stream_) {
     if (!p || !z || !g_out || n < 1) return fail(DIBS_ERR_INVALID_ARG, "dibs_particle_to_g_lim: bad arguments");
-    return launch_edge_probs(p, z, n, 0.0f, nullptr, g_out, (cudaStream_t)stream_);
+    return launch_edge_probs(p, z, p->Dz, n, 0.0f, nullptr, g_out, 0, (cudaStream_t)stream_);
 }
 
 extern "C" int dibs_sample_graphs(dibs_plan* p, const float* probs, const uint32_t* keys, int32_t n, int32_t n_samples,

@@ -35,6 +35,7 @@ struct McParams {
     float s2, log2pis2;                  // (sqrt(obs_noise))^2 and log(2 pi s2)
     float mean_edge, sig2_edge, lognorm_edge;   // N(theta; mean_edge, sig_edge): sig^2, log(2 pi sig^2)
     int hidden, hp;                      // DenseNN: H and next pow2 >= H
+    int activation;                      // DenseNN: 0 relu, 1 tanh, 2 sigmoid, 3 leakyrelu(0.01)  (stax, nonlinearGaussian.py:52-61)
     // BGe
     const double* bge_r;                 // [d or 1][d][d] fp64 R_j
     int bge_r_stride;                    // d*d if per-node R (interventions), 0 if shared

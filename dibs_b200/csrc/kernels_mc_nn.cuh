@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(nn_max_threads<DMAX>()) k_mc_nn(const __grid_c
             float gb1 = 0.0f, gw2 = 0.0f, gb2 = 0.0f, ssq = 0.0f;
             // ---- forward + backward over the observations, two per iteration (independent chains)
             const float onf = on ? 1.0f : 0.0f;
+            const int actk = p.activation;
             auto body = [&](int n0, auto two_c) {
                 constexpr bool TWO = decltype(two_c)::value;
                 const ulonglong2* xa = reinterpret_cast<const ulonglong2*>(sX + (size_t)n0 * DMAX);
@@ -187,7 +188,20 @@ __global__ void __launch_bounds__(nn_max_threads<DMAX>()) k_mc_nn(const __grid_c
                 }
                 const f32x2 pa = add2(pa0, pa1), pb = add2(pb0, pb1);
                 const float pre_a = lo2(pa) + hi2(pa), pre_b = lo2(pb) + hi2(pb);
-                const float act_a = fmaxf(pre_a, 0.0f), act_b = fmaxf(pre_b, 0.0f);
+                float act_a, act_b, dact_a, dact_b;          // activation and its derivative (stax Relu / Tanh / Sigmoid / LeakyRelu)
+                if (actk == 0) {
+                    act_a = fmaxf(pre_a, 0.0f); act_b = fmaxf(pre_b, 0.0f);
+                    dact_a = pre_a > 0.0f ? 1.0f : 0.0f; dact_b = pre_b > 0.0f ? 1.0f : 0.0f;
+                } else if (actk == 1) {
+                    act_a = tanhf(pre_a); act_b = tanhf(pre_b);
+                    dact_a = 1.0f - act_a * act_a; dact_b = 1.0f - act_b * act_b;
+                } else if (actk == 2) {
+                    act_a = sigmoidf_ref(pre_a); act_b = sigmoidf_ref(pre_b);
+                    dact_a = act_a * (1.0f - act_a); dact_b = act_b * (1.0f - act_b);
+                } else {
+                    act_a = pre_a >= 0.0f ? pre_a : 0.01f * pre_a; act_b = pre_b >= 0.0f ? pre_b : 0.01f * pre_b;
+                    dact_a = pre_a >= 0.0f ? 1.0f : 0.01f; dact_b = pre_b >= 0.0f ? 1.0f : 0.01f;
+                }
                 const float part_a = act_a * w2, part_b = act_b * w2;
                 float mean_a = b2, mean_b = b2;
                 if (HC > 0) {
@@ -208,8 +222,8 @@ __global__ void __launch_bounds__(nn_max_threads<DMAX>()) k_mc_nn(const __grid_c
                 ssq = fmaf(ra, ra, ssq);
                 if (TWO) ssq = fmaf(rb, rb, ssq);
                 const float da = ra * inv_s2, db = rb * inv_s2;
-                const float dpa = (pre_a > 0.0f) ? da * w2 : 0.0f;
-                const float dpb = (TWO && pre_b > 0.0f) ? db * w2 : 0.0f;
+                const float dpa = (actk == 0) ? (pre_a > 0.0f ? da * w2 : 0.0f) : da * w2 * dact_a;
+                const float dpb = !TWO ? 0.0f : ((actk == 0) ? (pre_b > 0.0f ? db * w2 : 0.0f) : db * w2 * dact_b);
                 const f32x2 dpa2 = pack2(dpa, dpa), dpb2 = pack2(dpb, dpb);
 #pragma unroll
                 for (int ip = 0; ip < NP; ++ip) {

@@ -299,9 +299,11 @@ inline int edge_probs_warps(int d, int k) {
     return w < 1 ? 1 : (w > EP_WARPS ? EP_WARPS : w);
 }
 
+// raw != 0: write the raw scores U V^T themselves (the step's edge-probability pass: the gradient kernels of the next
+// step apply sigma(alpha .) with the reference's rounding in their prologues)
 __global__ void __launch_bounds__(EP_WARPS * 32) k_edge_probs(const float* __restrict__ z, int z_ld, int n, int d, int k,
                                                              float alpha, float* __restrict__ p_out,
-                                                             int32_t* __restrict__ g_lim_out) {
+                                                             int32_t* __restrict__ g_lim_out, int raw) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ld = (d + 3) & ~3, tq = ld >> 2;                 // tq x tq register tiles of 4 x 4
@@ -360,7 +362,10 @@ __global__ void __launch_bounds__(EP_WARPS * 32) k_edge_probs(const float* __res
                 for (int b = 0; b < 4; ++b) {
                     const int i = 4 * ti + a, j = 4 * tj + b;
                     float v;
-                    if (p_out) v = (i == j) ? 0.0f : sigmoidf_ref(alpha * acc[a][b]);
+                    if (raw) v = acc[a][b];
+                    // stand-alone probabilities: fast exponential + approximate division (~1e-6 relative; the bit-exact
+                    // Bernoulli thresholds of the step never come from here)
+                    else if (p_out) v = (i == j) ? 0.0f : __fdividef(1.0f, 1.0f + __expf(-alpha * acc[a][b]));
                     else v = __int_as_float((i != j && acc[a][b] > 0.0f) ? 1 : 0);
                     if (i < d && j < d) sP[i * d + j] = v;                                      // packed [d][d]
                 }

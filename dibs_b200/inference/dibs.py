@@ -161,6 +161,7 @@ class DiBS:
         c.n_grad_mc_samples = self.n_grad_mc_samples
         c.n_acyclicity_mc_samples = self.n_acyclicity_mc_samples
         c.hidden = getattr(lm, "hidden", 0) if lm.native_kind == "densenn" else 0
+        c.activation = nat.ACTIVATION[getattr(lm, "activation", "relu")] if lm.native_kind == "densenn" else 0
         c.prng_partitionable = int(self.prng_partitionable)
         c.alpha_linear, c.beta_linear, c.tau = self.alpha_linear, self.beta_linear, self.tau
         c.score_function_baseline = self.score_function_baseline

@@ -1,7 +1,8 @@
 """Dense nonlinear-Gaussian likelihood plugin: plain descriptor the native plan consumes.
 
 Mirrors the constructor of the reference (dibs/models/nonlinearGaussian.py:105-135).  Natively implemented:
-one hidden layer, ReLU, with bias (the reference's default in dibs/target.py:270-271); anything else raises
+one hidden layer with bias (the reference's default in dibs/target.py:270-271) and any of its four activations
+(relu / tanh / sigmoid / leakyrelu, nonlinearGaussian.py:52-61); anything else raises
 like an unknown plugin would.  The forward/backward math (nonlinearGaussian.py:248-326) runs in
 dibs_b200/csrc/kernels_mc_nn.cuh, the stax initialisation (:155-186) in kernels_init.cuh.
 """
@@ -21,9 +22,9 @@ class DenseNonlinearGaussian:
         self.bias = bias
 
     def check_native(self):
-        if len(self.hidden_layers) != 1 or self.activation != 'relu' or not self.bias:
-            raise NotImplementedError("dibs_b200 implements DenseNonlinearGaussian with one hidden layer, "
-                                      "activation='relu', bias=True (SURVEY 8f rank 3 lists the rest)")
+        if len(self.hidden_layers) != 1 or not self.bias:
+            raise NotImplementedError("dibs_b200 implements DenseNonlinearGaussian with one hidden layer and bias=True, "
+                                      "any of the reference's activations (SURVEY 8f rank 3 lists the rest)")
 
     @property
     def hidden(self):

@@ -18,7 +18,8 @@
  *   Z      float32 [n_particles, n_vars, n_dim, 2]   (U, V interleaved innermost)
  *   Theta  float32 [n_particles, theta_dim]          flattened per particle:
  *            LinearGaussian:         theta[i, j]                       (d*d)
- *            DenseNonlinearGaussian: W1[j,i,h] | b1[j,h] | W2[j,h] | b2[j]   (hidden_layers=(H,))
+ *            DenseNonlinearGaussian: W1[j,i,h] | b1[j,h] | W2[j,h] | b2[j]   (hidden_layers=(H,), any of the
+ *                                    reference's four activations)
  *   keys   uint32  [.., 2]                           JAX threefry keys
  *   G      int32   [.., n_vars, n_vars]
  */
@@ -44,6 +45,7 @@ enum { DIBS_LIK_BGE = 0, DIBS_LIK_LINEAR_GAUSSIAN = 1, DIBS_LIK_DENSE_NONLINEAR_
 enum { DIBS_PRIOR_ERDOS_RENYI = 0, DIBS_PRIOR_SCALE_FREE = 1, DIBS_PRIOR_UNIFORM = 2 };
 enum { DIBS_ESTIMATOR_SCORE = 0, DIBS_ESTIMATOR_REPARAM = 1 };
 enum { DIBS_OPT_GD = 0, DIBS_OPT_RMSPROP = 1 };
+enum { DIBS_ACT_RELU = 0, DIBS_ACT_TANH = 1, DIBS_ACT_SIGMOID = 2, DIBS_ACT_LEAKYRELU = 3 };
 
 /* POD mirror of the constructor arguments of MarginalDiBS / JointDiBS
  * (dibs/inference/svgd.py:60-77, 425-442) and of the plugin objects they receive. */
@@ -72,6 +74,7 @@ typedef struct dibs_config {
     /* particle sharding (one process per GPU) */
     int32_t world_size;                /* number of ranks (1 = single GPU)                     */
     int32_t rank;                      /* this rank owns particles [rank*M/W, (rank+1)*M/W)    */
+    int32_t activation;                /* DenseNonlinearGaussian(activation=): DIBS_ACT_* (nonlinearGaussian.py:52-61) */
 } dibs_config;
 
 typedef struct dibs_plan dibs_plan;

@@ -68,6 +68,7 @@ class Likelihood:
     # DenseNonlinearGaussian (nonlinearGaussian.py:105-111)
     hidden: int = 5
     sig_param: float = 1.0
+    activation: str = "relu"  # 'relu' | 'tanh' | 'sigmoid' | 'leakyrelu' (stax, nonlinearGaussian.py:52-61)
 
     def theta_dim(self):
         d = self.n_vars
@@ -268,7 +269,17 @@ def densenn_logjoint(g, theta_flat, x, mask, lik, dt, want_grads=True):
     gt = np.swapaxes(g, 1, 2)                           # gt[s,j,i] = g[s,i,j]
     w1m = gt[..., None] * w1[None]                      # [S,j,i,h]
     pre = np.einsum("ni,sjih->sjnh", x, w1m) + b1[None, :, None, :]
-    act = np.maximum(pre, dt(0))
+    kind = getattr(lik, "activation", "relu")
+    if kind == "relu":
+        act, dact = np.maximum(pre, dt(0)), (pre > 0).astype(dt)
+    elif kind == "tanh":
+        act = np.tanh(pre); dact = 1 - act * act
+    elif kind == "sigmoid":
+        act = sigmoid(pre); dact = act * (1 - act)
+    elif kind == "leakyrelu":
+        act, dact = np.where(pre >= 0, pre, dt(0.01) * pre), np.where(pre >= 0, dt(1), dt(0.01))
+    else:
+        raise KeyError(f"Invalid activation function `{kind}`")
     mean = np.einsum("sjnh,jh->snj", act, w2) + b2[None, None, :]
     res = np.where(mask[None].astype(bool), dt(0), x[None] - mean)
     logp_all = -(np.log(dt(2.0 * np.pi) * s2) + res * res / s2) / dt(2.0)
@@ -283,7 +294,7 @@ def densenn_logjoint(g, theta_flat, x, mask, lik, dt, want_grads=True):
         return lp, None, None
     sp2 = dt(dt(lik.sig_param) * dt(lik.sig_param))
     delta = res / s2                                    # [S,n,j]
-    dpre = np.einsum("snj,jh->sjnh", delta, w2) * (pre > 0)
+    dpre = np.einsum("snj,jh->sjnh", delta, w2) * dact
     dw1 = np.einsum("ni,sjnh->sjih", x, dpre) * gt[..., None] + gt[..., None] * (-w1 / sp2)[None]
     db1 = dpre.sum(axis=2) - (b1 / sp2)[None]
     dw2 = np.einsum("snj,sjnh->sjh", delta, act) - (w2 / sp2)[None]

@@ -70,7 +70,7 @@ def make_prior(kind, d, epn):
 
 def make_case(name, *, lik, prior="er", epn=1, d=5, n_obs=20, m=3, s=8, a=4, t=7, hidden=4, interv=False,
               estimator=None, baseline=0.0, optimizer="rmsprop", n_dim=None, seed=0, alpha_linear=None,
-              tau=1.0, beta_linear=1.0):
+              tau=1.0, beta_linear=1.0, activation="relu"):
     rng = np.random.default_rng(seed)
     if lik == "densenn":
         data = make_nonlinear_gaussian_data(seed=seed, n_vars=d, n_observations=n_obs, n_edges_per_node=1, hidden=hidden)
@@ -97,7 +97,7 @@ def make_case(name, *, lik, prior="er", epn=1, d=5, n_obs=20, m=3, s=8, a=4, t=7
         lm = LinearGaussian(n_vars=d)
         model = JointDiBS(likelihood_model=lm, **kw)
     else:
-        lm = DenseNonlinearGaussian(n_vars=d, hidden_layers=(hidden,))
+        lm = DenseNonlinearGaussian(n_vars=d, hidden_layers=(hidden,), activation=activation)
         model = JointDiBS(likelihood_model=lm, **kw)
 
     key = random.PRNGKey(seed + 11)
@@ -118,7 +118,7 @@ def make_case(name, *, lik, prior="er", epn=1, d=5, n_obs=20, m=3, s=8, a=4, t=7
                lik=np.array(lik), prior=np.array(prior), n_edges_per_node=np.int32(epn),
                estimator=np.array(model.grad_estimator_z), score_function_baseline=np.float32(baseline),
                optimizer=np.array(optimizer), alpha_linear=np.float32(model.alpha(1)), beta_linear=np.float32(beta_linear),
-               tau=np.float32(tau), latent_prior_std=npy(model.latent_prior_std))
+               tau=np.float32(tau), latent_prior_std=npy(model.latent_prior_std), activation=np.array(activation))
     if joint:
         out["theta"] = flat_theta(theta, lik)
 
@@ -253,6 +253,11 @@ if __name__ == "__main__":
               interv=True, seed=7, alpha_linear=0.3)
     make_case("step_joint_densenn_er", lik="densenn", prior="er", epn=1, d=5, m=3, s=8, a=4, t=6, hidden=4, seed=4)
     make_case("step_joint_densenn_sf_interv", lik="densenn", prior="sf", d=6, m=3, s=7, a=3, t=9, hidden=5, interv=True, seed=5)
+    # the other activations of the reference's MLP (nonlinearGaussian.py:52-61)
+    make_case("step_joint_densenn_tanh", lik="densenn", prior="er", epn=1, d=5, m=3, s=8, a=4, t=6, hidden=4, seed=8, activation="tanh")
+    make_case("step_joint_densenn_sigmoid", lik="densenn", prior="sf", d=4, m=3, s=6, a=4, t=5, hidden=3, seed=9, activation="sigmoid")
+    make_case("step_joint_densenn_leakyrelu", lik="densenn", prior="er", epn=1, d=5, m=3, s=8, a=4, t=8, hidden=5, interv=True, seed=10,
+              activation="leakyrelu")
     # BASELINE.json configs[0]: MarginalDiBS BGe n_vars=5 n_particles=4 steps=50 (sf prior because ER p>=1 at d=5)
     make_sample_case("sample_c1_marginal_bge", lik="bge", prior="sf", epn=2, d=5, n_obs=100, m=4, s=128, a=32, steps=50,
                      callback_every=10)

@@ -17,6 +17,9 @@ STEP_CASES = [
     "step_joint_lingauss_score",
     "step_joint_densenn_er",
     "step_joint_densenn_sf_interv",
+    "step_joint_densenn_tanh",
+    "step_joint_densenn_sigmoid",
+    "step_joint_densenn_leakyrelu",
 ]
 SAMPLE_CASES = ["sample_c1_marginal_bge", "sample_joint_lingauss", "sample_joint_densenn"]
 
@@ -29,7 +32,8 @@ def oracle_config(g, sample_case=False):
     """Fixture dict -> oracle Config (constructor defaults of the reference classes where not stored)."""
     lik_kind = str(g["lik"])
     d = g["x"].shape[1]
-    lik = orc.Likelihood(kind=lik_kind, n_vars=d, hidden=int(g["hidden"]))
+    lik = orc.Likelihood(kind=lik_kind, n_vars=d, hidden=int(g["hidden"]),
+                         activation=str(g["activation"]) if "activation" in g else "relu")
     prior = orc.GraphPrior(kind=str(g["prior"]), n_vars=d, n_edges_per_node=int(g["n_edges_per_node"]))
     joint = lik_kind != "bge"
     cfg = orc.Config(lik=lik, prior=prior, joint=joint,

@@ -37,7 +37,8 @@ def build_model(g, sample_case=False, **over):
         return MarginalDiBS(likelihood_model=BGe(n_vars=d), **kw)
     if lik == "lingauss":
         return JointDiBS(likelihood_model=LinearGaussian(n_vars=d), **kw)
-    return JointDiBS(likelihood_model=DenseNonlinearGaussian(n_vars=d, hidden_layers=(int(g["hidden"]),)), **kw)
+    act = str(g["activation"]) if "activation" in g else "relu"
+    return JointDiBS(likelihood_model=DenseNonlinearGaussian(n_vars=d, hidden_layers=(int(g["hidden"]),), activation=act), **kw)
 
 
 def npy(t):

@@ -34,8 +34,11 @@ def main(rep, workload, out):
         for pat, ph in PHASE_OF:
             if name.startswith(pat) or ("::" + pat) in name or pat in name:
                 if ph is None:
-                    # the MC pass kernels alternate theta / z within a joint step (launch order of enqueue_grads)
-                    ph = "mc_theta" if ("MODE=0" in name or "<0>" in name or ", 0>" in name or "(int)0>" in name) else "mc_z"
+                    # Monte-Carlo pass kernels: the MODE template argument (2nd) tells the Theta pass (0) from the Z pass
+                    import re
+                    mm = re.search(r"k_mc_\w+<(?:\(int\))?\d+, (?:\(int\))?(\d)", name)
+                    mode = int(mm.group(1)) if mm else 1
+                    ph = "mc_theta" if mode == 0 else "mc_z"
                     mc_seen += 1
                 per.setdefault(ph, []).append(b)
                 break
