@@ -1656,3 +1656,12 @@ extern "C" int dibs_prng_split(const uint32_t* key_host, int32_t num, int32_t pa
     }
     return DIBS_OK;
 }
+
+#ifdef DIBS_PHI_TRACE
+// debug builds only (python -m dibs_b200.build is never run with this macro): copy out the phi pipeline trace
+extern "C" int dibs_debug_phi_trace(unsigned long long* out_host, int n_words) {
+    cudaDeviceSynchronize();
+    CU(cudaMemcpyFromSymbol(out_host, g_phi_trace, (size_t)n_words * sizeof(unsigned long long)));
+    return DIBS_OK;
+}
+#endif

@@ -50,7 +50,7 @@ __device__ __forceinline__ void row_times_smem(const float (&x)[DMAX], const flo
 constexpr int ACYC_SLOTS = 8;
 
 template <int DMAX>
-__global__ void __launch_bounds__(8 * DMAX, (DMAX <= 20 ? 3 : 2)) k_acyclic_rows(const __grid_constant__ AcycParams p) {
+__global__ void __launch_bounds__(8 * DMAX, (DMAX <= 20 ? 5 : 2)) k_acyclic_rows(const __grid_constant__ AcycParams p) {
     extern __shared__ __align__(16) float smem[];
     static_assert(DMAX % 4 == 0 && DMAX <= 32, "128-bit row loads");
     const int d = p.d, dd = d * d;
@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(8 * DMAX, (DMAX <= 20 ? 3 : 2)) k_acyclic_rows
     float* sS = smem;                                   // [d*d] alpha*scores, or exp(-alpha*scores) when tau == 1
     float* sM = sS + ((dd + 3) & ~3);                   // [SLOTS][DMAX][DMAX]  I + G/d of each sample (then its running square)
     float* sF = sM + ACYC_SLOTS * MAT;                  // [SLOTS][DMAX][DMAX]  tau alpha G (1 - G)
+    float* sR = sF + ACYC_SLOTS * MAT + tid * DMAX;     // [threads][DMAX]      this thread's row of the running result
 
     const bool fast_soft = p.tau == 1.0f;
     for (int e = tid; e < dd; e += blockDim.x) {
@@ -69,8 +70,10 @@ __global__ void __launch_bounds__(8 * DMAX, (DMAX <= 20 ? 3 : 2)) k_acyclic_rows
         sS[e] = fast_soft ? expf(-a) : a;
     }
     const uint2 key = make_uint2(p.keys_override[2 * m], p.keys_override[2 * m + 1]);
-    // zero the padding once (rows / columns >= d are never written again)
-    for (int e = tid; e < 2 * ACYC_SLOTS * MAT; e += blockDim.x) sM[e] = 0.0f;
+    // zero the padding once (rows / columns >= d are never written again); none at n_vars == DMAX
+    if (d < DMAX)
+        for (int e = tid; e < 2 * ACYC_SLOTS * MAT / 4; e += blockDim.x)
+            reinterpret_cast<float4*>(sM)[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     __syncthreads();
 
     const float inv_d = 1.0f / (float)d, inv_dd = 1.0f / (float)dd;
@@ -125,7 +128,10 @@ __global__ void __launch_bounds__(8 * DMAX, (DMAX <= 20 ? 3 : 2)) k_acyclic_rows
     const int row = valid ? tid - slot_raw * d : 0;     // idle threads shadow (slot 0, row 0) and never write
     float* Zs = sM + slot * MAT;
     const float* Fs = sF + slot * MAT;
-    float zr[DMAX], res[DMAX], out[DMAX];
+    // the result row is parked in shared memory between its (few) products: 20 registers less, which is what lets a
+    // fourth CTA fit on the SM at n_vars = 20 (strip stride DMAX floats: conflict-free 128-bit accesses)
+    float zr[DMAX], out[DMAX];
+    float4* resv = reinterpret_cast<float4*>(sR);
     {
         const float4* src = reinterpret_cast<const float4*>(Zs + row * DMAX);
 #pragma unroll
@@ -142,12 +148,18 @@ __global__ void __launch_bounds__(8 * DMAX, (DMAX <= 20 ? 3 : 2)) k_acyclic_rows
         if (n & 1) {
             if (!have_res) {
 #pragma unroll
-                for (int j = 0; j < DMAX; ++j) res[j] = zr[j];
+                for (int q = 0; q < DMAX / 4; ++q) resv[q] = make_float4(zr[4 * q], zr[4 * q + 1], zr[4 * q + 2], zr[4 * q + 3]);
                 have_res = true;
             } else {
+                float res[DMAX];
+#pragma unroll
+                for (int q = 0; q < DMAX / 4; ++q) {
+                    const float4 v = resv[q];
+                    res[4 * q] = v.x; res[4 * q + 1] = v.y; res[4 * q + 2] = v.z; res[4 * q + 3] = v.w;
+                }
                 row_times_smem<DMAX>(res, Zs, d, out);
 #pragma unroll
-                for (int j = 0; j < DMAX; ++j) res[j] = out[j];
+                for (int q = 0; q < DMAX / 4; ++q) resv[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
             }
         }
         n >>= 1;
@@ -170,8 +182,13 @@ __global__ void __launch_bounds__(8 * DMAX, (DMAX <= 20 ? 3 : 2)) k_acyclic_rows
     float* sRed = sM;                                      // [SLOTS][d*d]
     if (valid) {
 #pragma unroll
+        for (int q = 0; q < DMAX / 4; ++q) {
+            const float4 v = resv[q];
+            out[4 * q] = v.x; out[4 * q + 1] = v.y; out[4 * q + 2] = v.z; out[4 * q + 3] = v.w;
+        }
+#pragma unroll
         for (int j = 0; j < DMAX; ++j)
-            if (j < d) sRed[(size_t)slot * dd + j * d + row] = (d == 1) ? Fs[j * DMAX + row] : res[j] * Fs[j * DMAX + row];
+            if (j < d) sRed[(size_t)slot * dd + j * d + row] = (d == 1) ? Fs[j * DMAX + row] : out[j] * Fs[j * DMAX + row];
     }
     __syncthreads();
     // deterministic reduction over the chunk's samples, in slot order
@@ -185,7 +202,7 @@ __global__ void __launch_bounds__(8 * DMAX, (DMAX <= 20 ? 3 : 2)) k_acyclic_rows
 }
 
 inline size_t acyclic_rows_smem(int d, int dmax) {
-    return ((((size_t)d * d + 3) & ~(size_t)3) + (size_t)2 * ACYC_SLOTS * dmax * dmax + 4) * sizeof(float);
+    return ((((size_t)d * d + 3) & ~(size_t)3) + (size_t)2 * ACYC_SLOTS * dmax * dmax + (size_t)ACYC_SLOTS * dmax * dmax + 4) * sizeof(float);
 }
 inline int acyclic_rows_threads(int d) { return ((ACYC_SLOTS * d + 31) / 32) * 32; }
 

@@ -176,98 +176,112 @@ constexpr int PT_C = 64, PT_J = 32;
 // fixed-order sum of the slice planes -> phi = -(sum)/M (svgd.py:212-216), RMSprop / SGD step (svgd.py:265,718-719;
 // jax.example_libraries.optimizers), updated rows to this rank's next buffer and -- on several GPUs -- to every
 // peer's.  16 consecutive threads cover one row's 64 columns: 128-bit accesses, 256 contiguous bytes per row.
+// optimizer step of one element (IEEE-ordered like jax.example_libraries.optimizers; svgd.py:265,718-719)
+__device__ __forceinline__ void phi_opt_step(int optimizer, float stepsize, float phi, float x, float v, float& xn, float& vn) {
+    if (optimizer == 1) {
+        // rmsprop(step, gamma=0.9, eps=1e-8): v = v*gamma + g^2*(1-gamma); x -= step*g/sqrt(v+eps)
+        vn = __fadd_rn(__fmul_rn(v, 0.9f), __fmul_rn(__fmul_rn(phi, phi), 0.1f));
+        xn = __fsub_rn(x, __fdiv_rn(__fmul_rn(stepsize, phi), __fsqrt_rn(__fadd_rn(vn, 1e-8f))));
+    } else {
+        vn = 0.0f;
+        xn = __fsub_rn(x, __fmul_rn(stepsize, phi));   // sgd: x - step * g
+    }
+}
+
+// elements [gc, min(gc + 4, c_end)) of row gi, one at a time: tile edges and layouts whose rows are not 16-byte
+// aligned (odd n_vars).  Deliberately out of line and rolled -- see phi_finish_tile on code size
+static __device__ __noinline__ void phi_finish_scalar(const PairParams& p, int gi, int gc, int c_end, int D, size_t plane,
+                                                      float inv_m, bool rms) {
+#pragma unroll 1
+    for (int c = gc; c < min(gc + 4, c_end); ++c) {
+        const float* pr = p.phi_part + (size_t)gi * D + c;
+        float sum = 0.0f;
+#pragma unroll 1
+        for (int s = 0; s < p.n_jsplit; ++s) sum += __ldcg(pr + (size_t)s * plane);
+        const float phi = -sum * inv_m;                      // -(weighted_gradient_ascent + repulsion).mean(axis=0)
+        if (p.phi_out) p.phi_out[(size_t)gi * p.phi_ld + c] = phi;
+        if (!p.x_next) continue;
+        float* vp = rms ? p.v + (size_t)gi * p.v_ld + c : nullptr;
+        float xn, vn;
+        phi_opt_step(p.optimizer, p.stepsize, phi, p.x_all[(size_t)(p.row0 + gi) * p.ld + c], rms ? *vp : 0.0f, xn, vn);
+        if (rms) *vp = vn;
+        p.x_next[(size_t)gi * p.next_ld + c] = xn;
+        if (p.push_x.world) peer_store(p.push_x, (size_t)(p.row0 + gi) * p.next_ld + c, xn);
+    }
+}
+
+struct PhiFinishLoads { float4 q[4], x, v; };
+
+// The tile's last-arriving CTA runs this ONCE: it is cold code, and what it costs is instruction fetch (the SM's
+// 32 KB instruction cache holds the main loop; an earlier, fully unrolled version of this pass was 65 KB of SASS and
+// took 25 us per 128 x 64 tile, hardly any of it memory latency).  Hence: ONE rolled loop over 4-column items,
+// software-pipelined by hand -- the (up to) six 128-bit reads of the next item are issued before the current one is
+// finished -- and everything irregular pushed into phi_finish_scalar.
 __device__ __forceinline__ void phi_finish_tile(const PairParams& p, int i0, int tile_rows, int c0, int c_end, int tid, int nthr) {
     const int D = p.dz + p.dth;
     const size_t plane = (size_t)p.n_rows * D;
     const float inv_m = 1.0f / (float)p.n_all;
-    for (int idx = tid; idx < tile_rows * 16; idx += nthr) {
+    const int limit = tile_rows * 16, n_jsplit = p.n_jsplit;
+    const bool rms = p.x_next && p.optimizer == 1;
+    // 128-bit path: every row of every buffer the item touches starts 16-byte aligned
+    const bool aligned = (((D | p.ld | (p.x_next ? p.next_ld : 0) | (rms ? p.v_ld : 0) | c0) & 3) == 0) && ((plane & 3) == 0) &&
+                         (((reinterpret_cast<uintptr_t>(p.phi_part) | reinterpret_cast<uintptr_t>(p.x_all) |
+                            reinterpret_cast<uintptr_t>(p.x_next) | reinterpret_cast<uintptr_t>(p.v)) & 15) == 0) && !p.phi_out;
+    auto vec_item = [&](int idx) -> bool {
         const int gi = i0 + (idx >> 4), gc = c0 + (idx & 15) * 4;
-        if (gi >= p.n_rows || gc >= c_end) continue;
-        const bool full = gc + 3 < c_end;
-        float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        return idx < limit && aligned && gi < p.n_rows && gc + 3 < c_end;
+    };
+    auto load = [&](PhiFinishLoads& L, int idx) {
+        if (!vec_item(idx)) return;
+        const int gi = i0 + (idx >> 4), gc = c0 + (idx & 15) * 4;
         const float* pr = p.phi_part + (size_t)gi * D + gc;
-        if (full && ((plane | ((size_t)gi * D + gc)) & 3) == 0) {
-#pragma unroll 8
-            for (int s = 0; s < p.n_jsplit; ++s) {
-                const float4 v4 = __ldcg(reinterpret_cast<const float4*>(pr + (size_t)s * plane));
-                sum[0] += v4.x; sum[1] += v4.y; sum[2] += v4.z; sum[3] += v4.w;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (u < n_jsplit) L.q[u] = __ldcg(reinterpret_cast<const float4*>(pr + (size_t)u * plane));
+        L.x = *reinterpret_cast<const float4*>(p.x_all + (size_t)(p.row0 + gi) * p.ld + gc);
+        if (rms) L.v = *reinterpret_cast<const float4*>(p.v + (size_t)gi * p.v_ld + gc);
+    };
+    PhiFinishLoads cur, nxt;
+    load(cur, tid);
+#pragma unroll 1
+    for (int idx = tid; idx < limit; idx += nthr) {
+        load(nxt, idx + nthr);
+        const int gi = i0 + (idx >> 4), gc = c0 + (idx & 15) * 4;
+        if (vec_item(idx)) {
+            float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (u < n_jsplit) { sum[0] += cur.q[u].x; sum[1] += cur.q[u].y; sum[2] += cur.q[u].z; sum[3] += cur.q[u].w; }
+#pragma unroll 1
+            for (int s = 4; s < n_jsplit; ++s) {               // more than four slices: the rest in order
+                const float4 q = __ldcg(reinterpret_cast<const float4*>(p.phi_part + (size_t)s * plane + (size_t)gi * D + gc));
+                sum[0] += q.x; sum[1] += q.y; sum[2] += q.z; sum[3] += q.w;
             }
-        } else {
-            for (int s = 0; s < p.n_jsplit; ++s) {
+            const float xc[4] = {cur.x.x, cur.x.y, cur.x.z, cur.x.w};
+            const float vo[4] = {rms ? cur.v.x : 0.0f, rms ? cur.v.y : 0.0f, rms ? cur.v.z : 0.0f, rms ? cur.v.w : 0.0f};
+            float xn[4], vn[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (gc + u < c_end) sum[u] += __ldcg(pr + (size_t)s * plane + u);
-            }
-        }
-        const float* xr = p.x_all + (size_t)(p.row0 + gi) * p.ld + gc;
-        float xc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        if (full && ((reinterpret_cast<uintptr_t>(xr) & 15) == 0)) {
-            const float4 x4 = *reinterpret_cast<const float4*>(xr);
-            xc[0] = x4.x; xc[1] = x4.y; xc[2] = x4.z; xc[3] = x4.w;
-        } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) if (gc + u < c_end) xc[u] = xr[u];
-        }
-        float phi[4], xn[4], vn[4];
-        float* vp = p.v ? p.v + (size_t)gi * p.v_ld + gc : nullptr;
-        const bool vec_v = full && p.x_next && p.optimizer == 1 && ((((size_t)gi * p.v_ld + gc) & 3) == 0);
-        float vo[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        if (p.x_next && p.optimizer == 1) {
-            if (vec_v) { const float4 v4 = *reinterpret_cast<const float4*>(vp); vo[0] = v4.x; vo[1] = v4.y; vo[2] = v4.z; vo[3] = v4.w; }
-            else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) if (gc + u < c_end) vo[u] = vp[u];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            // -(weighted_gradient_ascent + repulsion).mean(axis=0)   (svgd.py:212-216)
-            phi[u] = -sum[u] * inv_m;
-            if (p.optimizer == 1) {
-                // rmsprop(step, gamma=0.9, eps=1e-8): v = v*gamma + g^2*(1-gamma); x -= step*g/sqrt(v+eps)
-                vn[u] = __fadd_rn(__fmul_rn(vo[u], 0.9f), __fmul_rn(__fmul_rn(phi[u], phi[u]), 0.1f));
-                xn[u] = __fsub_rn(xc[u], __fdiv_rn(__fmul_rn(p.stepsize, phi[u]), __fsqrt_rn(__fadd_rn(vn[u], 1e-8f))));
-            } else {
-                vn[u] = 0.0f;
-                xn[u] = __fsub_rn(xc[u], __fmul_rn(p.stepsize, phi[u]));   // sgd: x - step * g
-            }
-        }
-        if (p.phi_out) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) if (gc + u < c_end) p.phi_out[(size_t)gi * p.phi_ld + gc + u] = phi[u];
-        }
-        if (p.x_next) {
-            if (p.optimizer == 1) {
-                if (vec_v) *reinterpret_cast<float4*>(vp) = make_float4(vn[0], vn[1], vn[2], vn[3]);
-                else {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) if (gc + u < c_end) vp[u] = vn[u];
-                }
-            }
-            const size_t off_loc = (size_t)gi * p.next_ld + gc;                    // in this rank's rows
-            const size_t off_all = (size_t)(p.row0 + gi) * p.next_ld + gc;         // in a whole particle buffer
-            if (full && (((uintptr_t)(p.x_next + off_loc)) & 15) == 0) {
+            for (int u = 0; u < 4; ++u) phi_opt_step(p.optimizer, p.stepsize, -sum[u] * inv_m, xc[u], vo[u], xn[u], vn[u]);
+            if (p.x_next) {
+                if (rms) *reinterpret_cast<float4*>(p.v + (size_t)gi * p.v_ld + gc) = make_float4(vn[0], vn[1], vn[2], vn[3]);
                 const float4 x4 = make_float4(xn[0], xn[1], xn[2], xn[3]);
-                *reinterpret_cast<float4*>(p.x_next + off_loc) = x4;
+                *reinterpret_cast<float4*>(p.x_next + (size_t)gi * p.next_ld + gc) = x4;
                 if (p.push_x.world) {
+                    const size_t off_all = (size_t)(p.row0 + gi) * p.next_ld + gc;      // in a whole particle buffer
 #pragma unroll 1
                     for (int q = 0; q < p.push_x.world; ++q)
                         if (q != p.push_x.rank) *reinterpret_cast<float4*>(p.push_x.dst[q] + off_all) = x4;
                 }
-            } else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (gc + u >= c_end) continue;
-                    p.x_next[off_loc + u] = xn[u];
-                    if (p.push_x.world) peer_store(p.push_x, off_all + u, xn[u]);
-                }
             }
+        } else if (gi < p.n_rows && gc < c_end) {
+            phi_finish_scalar(p, gi, gc, c_end, D, plane, inv_m, rms);
         }
+        cur = nxt;
     }
 }
 
 template <int RPT>
-__global__ void __launch_bounds__(128) k_phi(PairParams p) {
+__global__ void __launch_bounds__(128) k_phi(const __grid_constant__ PairParams p) {
     constexpr int PB_I = 8 * RPT;       // rows per tile
     constexpr int PB_KP = PB_I + 4;     // padded stride of the transposed K tiles [j][i]
     __shared__ __align__(16) float sK[PT_J * PB_KP];      // K_full[i][j] transposed: [j][i]

@@ -137,6 +137,14 @@ __device__ __forceinline__ void split_tf32(float4 v, float4& hi, float4& lo) {
     hi.w = tf32_rn(v.w); lo.w = v.w - hi.w;
 }
 
+#ifdef DIBS_PHI_TRACE
+// pipeline trace of a debug build (tools/phi_trace.py): 64 clock samples per CTA, never compiled into the product library
+__device__ unsigned long long g_phi_trace[1024 * 64];
+#define PHI_TR(slot) do { if (tr) tr[slot] = (unsigned long long)clock64(); } while (0)
+#else
+#define PHI_TR(slot) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(MM_THREADS, 1)
 k_phi_mma(const __grid_constant__ PairParams p, const __grid_constant__ PhiMmaMaps maps) {
     extern __shared__ uint8_t mm_smem_raw[];
@@ -151,6 +159,14 @@ k_phi_mma(const __grid_constant__ PairParams p, const __grid_constant__ PhiMmaMa
     __shared__ int s_last;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef DIBS_PHI_TRACE
+    const int tr_cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    unsigned long long* tr = tr_cta < 1024 ? g_phi_trace + tr_cta * 64 : nullptr;
+    if (tr && tid == 0) {
+        unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        tr[0] = global_timer_ns(); tr[1] = sm; tr[50] = (unsigned long long)clock64();
+    }
+#endif
     const int D = p.dz + p.dth;
     const int nzt = (p.dz + MM_COLS - 1) / MM_COLS;
     const bool z_block = (int)blockIdx.x < nzt;
@@ -197,6 +213,7 @@ k_phi_mma(const __grid_constant__ PairParams p, const __grid_constant__ PhiMmaMa
                 const int s = it % MM_STAGES;
                 if (it >= MM_STAGES) mbar_wait(bar_empty + s, ((it / MM_STAGES) - 1) & 1);
                 const int j0 = j_begin + it * MM_KS;
+                if (it < 8) PHI_TR(8 + it);
                 mbar_expect_tx(bar_full + s, bytes);
                 tma_load_2d(stage_ptr(s, 0), &maps.a[0], bar_full + s, j0, i0);
                 tma_load_2d(stage_ptr(s, 1), &maps.a[1], bar_full + s, j0, i0);
@@ -215,24 +232,29 @@ k_phi_mma(const __grid_constant__ PairParams p, const __grid_constant__ PhiMmaMa
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_tf32(MM_ROWS, MM_COLS);
             const uint32_t d1 = tmem_base, d2 = tmem_base + MM_COLS;
+            const uint64_t da_base = umma_desc_sw128(smem_u32(stage_ptr(0, 0)), 16, 1024);
+            const uint64_t db_base = umma_desc(smem_u32(stage_ptr(0, 4)), MM_B_BYTES / 2, 512, 1u);
             for (int it = 0; it < n_it; ++it) {
                 const int s = it % MM_STAGES;
                 mbar_wait(bar_split + s, (it / MM_STAGES) & 1);
+                if (it < 8) PHI_TR(32 + it);
                 tc_fence_after();
-                const uint32_t a1h = smem_u32(stage_ptr(s, 0)), a1l = smem_u32(stage_ptr(s, 1));
-                const uint32_t a2h = same_a ? a1h : smem_u32(stage_ptr(s, 2)), a2l = same_a ? a1l : smem_u32(stage_ptr(s, 3));
-                const uint32_t b1h = smem_u32(stage_ptr(s, 4)), b1l = smem_u32(stage_ptr(s, 5));
-                const uint32_t b2h = smem_u32(stage_ptr(s, 6)), b2l = smem_u32(stage_ptr(s, 7));
+                // descriptors of the stage's first K step (one thread issues everything: keep its instruction count low);
+                    // a K step adds a constant to the start-address field (16-byte units, no carry out of the 14 bits:
+                    // the stage buffers are far below 256 KB)
+                const uint64_t sa = (uint64_t)(((uint32_t)s * MM_STAGE_BYTES) >> 4);
+                const uint64_t ea1h = da_base + sa, ea1l = ea1h + (MM_A_BYTES >> 4);
+                const uint64_t ea2h = same_a ? ea1h : ea1h + 2 * (MM_A_BYTES >> 4), ea2l = same_a ? ea1l : ea1h + 3 * (MM_A_BYTES >> 4);
+                const uint64_t eb1h = db_base + sa, eb1l = eb1h + (MM_B_BYTES >> 4);
+                const uint64_t eb2h = eb1h + 2 * (MM_B_BYTES >> 4), eb2l = eb1h + 3 * (MM_B_BYTES >> 4);
 #pragma unroll
                 for (int ks = 0; ks < MM_KS / 8; ++ks) {
                     const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
                     // A: K-major, +32 B per K step inside the 128-byte swizzle row; SBO = 8 rows
-                    const uint64_t da1h = umma_desc_sw128(a1h + 32 * ks, 16, 1024), da1l = umma_desc_sw128(a1l + 32 * ks, 16, 1024);
-                    const uint64_t da2h = umma_desc_sw128(a2h + 32 * ks, 16, 1024), da2l = umma_desc_sw128(a2l + 32 * ks, 16, 1024);
+                    const uint64_t da1h = ea1h + 2 * ks, da1l = ea1l + 2 * ks, da2h = ea2h + 2 * ks, da2l = ea2l + 2 * ks;
                     // B: MN-major (SWIZZLE_128B_BASE32B atoms of 4 j x 128 B), +1024 B per K step (8 rows of 128 B);
                     // LBO = next 32-column panel, SBO = next 4 j
-                    const uint64_t db1h = umma_desc(b1h + 1024 * ks, MM_B_BYTES / 2, 512, 1u), db1l = umma_desc(b1l + 1024 * ks, MM_B_BYTES / 2, 512, 1u);
-                    const uint64_t db2h = umma_desc(b2h + 1024 * ks, MM_B_BYTES / 2, 512, 1u), db2l = umma_desc(b2l + 1024 * ks, MM_B_BYTES / 2, 512, 1u);
+                    const uint64_t db1h = eb1h + 64 * ks, db1l = eb1l + 64 * ks, db2h = eb2h + 64 * ks, db2l = eb2l + 64 * ks;
                     tc_mma_tf32(d1, da1h, db1h, idesc, acc);      // K G
                     tc_mma_tf32(d1, da1h, db1l, idesc, 1u);
                     tc_mma_tf32(d1, da1l, db1h, idesc, 1u);
@@ -241,6 +263,7 @@ k_phi_mma(const __grid_constant__ PairParams p, const __grid_constant__ PhiMmaMa
                     tc_mma_tf32(d2, da2l, db2h, idesc, 1u);
                 }
                 tc_commit(bar_empty + s);             // the stage may be refilled once these MMAs have read it
+                if (it < 8) PHI_TR(40 + it);
             }
             tc_commit(bar_accum);                     // accumulators complete
         }
@@ -252,6 +275,7 @@ k_phi_mma(const __grid_constant__ PairParams p, const __grid_constant__ PhiMmaMa
         for (int it = 0; it < n_it; ++it) {
             const int s = it % MM_STAGES;
             mbar_wait(bar_full + s, (it / MM_STAGES) & 1);
+            if (tid == 64 && it < 8) PHI_TR(16 + it);
             // K* tile (already split by the kernel that produced K): this thread's row of hi + lo, 8 chunks of 16 B each
             // -- logical chunk c sits at position c ^ (row & 7) -- summed in j order into the row sum
             {
@@ -279,21 +303,14 @@ k_phi_mma(const __grid_constant__ PairParams p, const __grid_constant__ PhiMmaMa
             fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core's async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_split + s);
+            if (tid == 64 && it < 8) PHI_TR(24 + it);
         }
         // ===== epilogue: TMEM -> registers -> partial plane of this j slice =====
-        mbar_wait(bar_accum, 0);
-        tc_fence_after();
-        const float c2 = -2.0f / h;
-        const size_t plane = (size_t)p.n_rows * D;
-        float* part = p.phi_part + (size_t)blockIdx.z * plane;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
-        // Global traffic of the epilogue goes through two shared-memory tiles (the operand stages are free now: every
-        // TMA load and every MMA has completed) so that rows are read and written 256 contiguous bytes at a time --
-        // one row per thread straight to global memory costs 32 sectors per instruction (measured: ~20 us per CTA)
-        constexpr int EP_LD = MM_COLS + 1;                        // odd stride: lane = row is conflict-free
-        float* sX = reinterpret_cast<float*>(smem);               // [128][65] the tile's own rows x_i
-        float* sO = sX + MM_ROWS * EP_LD;                         // [128][65] partial sums of this j slice
-        for (int idx = st; idx < MM_ROWS * (MM_COLS / 4); idx += 128) {
+        // the tile's own rows x_i are fetched while the last MMAs drain (registers are plentiful at one CTA per SM)
+        float4 xpre[MM_ROWS * (MM_COLS / 4) / 128];
+#pragma unroll
+        for (int w = 0; w < MM_ROWS * (MM_COLS / 4) / 128; ++w) {
+            const int idx = st + 128 * w;
             const int r = idx >> 4, c4 = (idx & 15) * 4;
             const int gi = i0 + r, gc = c0 + c4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -307,8 +324,26 @@ k_phi_mma(const __grid_constant__ PairParams p, const __grid_constant__ PhiMmaMa
                     if (gc + 3 < c_end) v.w = xr[3];
                 }
             }
-            float* d = sX + r * EP_LD + c4;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            xpre[w] = v;
+        }
+        mbar_wait(bar_accum, 0);
+        if (tid == 64) PHI_TR(48);
+        tc_fence_after();
+        const float c2 = -2.0f / h;
+        const size_t plane = (size_t)p.n_rows * D;
+        float* part = p.phi_part + (size_t)blockIdx.z * plane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
+        // Global traffic of the epilogue goes through two shared-memory tiles (the operand stages are free now: every
+        // TMA load and every MMA has completed) so that rows are read and written 256 contiguous bytes at a time --
+        // one row per thread straight to global memory costs 32 sectors per instruction (measured: ~20 us per CTA)
+        constexpr int EP_LD = MM_COLS + 1;                        // odd stride: lane = row is conflict-free
+        float* sX = reinterpret_cast<float*>(smem);               // [128][65] the tile's own rows x_i
+        float* sO = sX + MM_ROWS * EP_LD;                         // [128][65] partial sums of this j slice
+#pragma unroll
+        for (int w = 0; w < MM_ROWS * (MM_COLS / 4) / 128; ++w) {
+            const int idx = st + 128 * w;
+            float* d = sX + (idx >> 4) * EP_LD + (idx & 15) * 4;
+            d[0] = xpre[w].x; d[1] = xpre[w].y; d[2] = xpre[w].z; d[3] = xpre[w].w;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");           // the 128 epilogue threads
 #pragma unroll 1
@@ -339,6 +374,7 @@ k_phi_mma(const __grid_constant__ PairParams p, const __grid_constant__ PhiMmaMa
             }
         }
         tc_fence_before();
+        if (tid == 64) PHI_TR(49);
     }
     // ---- the tile's last j-slice CTA finishes: fixed-order sum of the slices -> phi, optimizer step, peer push
     __threadfence();
@@ -354,10 +390,16 @@ k_phi_mma(const __grid_constant__ PairParams p, const __grid_constant__ PhiMmaMa
         if (s_last) *cnt = 0u;
     }
     __syncthreads();
+#ifdef DIBS_PHI_TRACE
+    if (tr && tid == 0) { tr[51] = (unsigned long long)clock64(); tr[2] = global_timer_ns(); tr[3] = s_last; }
+#endif
     if (!s_last) return;
     __threadfence();
     phi_finish_tile(p, i0, MM_ROWS, c0, c_end, tid, MM_THREADS);
     if (p.push_x.world) peer_signal(p.push_x, gridDim.x * gridDim.y);
+#ifdef DIBS_PHI_TRACE
+    if (tr && tid == 0) { tr[52] = (unsigned long long)clock64(); tr[4] = global_timer_ns(); }
+#endif
 }
 
 }  // namespace dibs
