@@ -21,4 +21,8 @@ timeout 900 ncu --set full --clock-control none --import-source on \
     -k regex:'k_mc_lin_qr|k_acyclic_rows|k_phi|k_pair_dist|k_pair_finish|k_prologue|k_edge_probs' -s 14 -c 9 \
     -f -o $OUT/prof_t_lin_$TAG python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-also > $OUT/ncu_full_$TAG.log 2>&1
 tail -2 $OUT/ncu_full_$TAG.log
+if [ -f _exp/libdibs_b200_trace.so ]; then
+  echo "== phi pipeline trace (debug build of the library, tools/phi_trace.py)"
+  timeout 200 python tools/phi_trace.py _exp/libdibs_b200_trace.so t_lin > $OUT/phi_trace_t_lin_$TAG.txt 2>&1; tail -14 $OUT/phi_trace_t_lin_$TAG.txt
+fi
 ls -la $OUT | tail -12
