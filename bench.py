@@ -56,7 +56,13 @@ WORKLOADS = {
     "t_lin_q": ("JointDiBS LinearGaussian n_vars=20 n_particles=256 n_mc=128 (quarter of the target shape)", "lingauss", 20, 256, 128, 32, 0),
 }
 N_OBS = 100
-T_MID = 100          # time steps at mid-run t so alpha(t), beta(t) are non-degenerate (work per step is t-independent)
+# `value` is timed from step T_MID on freshly initialised particles, so that alpha(t), beta(t) are non-degenerate.
+# The work of a step is NOT t-independent for every model: LinearGaussian is flat, but a BGe step at t = 0 costs ~6x
+# (n_vars = 20) to ~20x (n_vars = 50) a step at t >= 100 (profiles/r02/RESULTS.md) -- which is why the line also carries
+# `value_from_t0` (the same device timing over steps 0..K-1 of re-initialised particles, what sample() actually runs) and
+# why `e2e`, which starts at t = 0 by construction, is the figure comparable to a real sample() call.  The CPU arm
+# (`cpu_baseline`, `--impl reference`) is timed at T_MID too: `value` and the CPU figure cover the same step range.
+T_MID = 100
 L2_FLUSH_BYTES = 256 << 20
 FP32_SIMT_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # theoretical; MEASURED_PEAKS.json has no fp32 SIMT figure
 
@@ -380,7 +386,7 @@ def load_traffic(name, world):
         return {}
 
 
-def measure_workload(ctx, name, K, W, n_prof, want_hot=True):
+def measure_workload(ctx, name, K, W, n_prof, want_hot=True, want_t0=None):
     """Device-timed steps of one workload with the state resident in HBM.  Returns a dict with value (steps/s, cold L2,
     max over ranks), ms_per_step, launches, per-kernel table and the roofline entry of the dominant kernel."""
     import ctypes
@@ -497,6 +503,22 @@ def measure_workload(ctx, name, K, W, n_prof, want_hot=True):
         step_ms_tl, tl_ms = steps_timed(t, n_tl, per_kernel=2); t += n_tl
         res["timeline_end_us"] = {ph: round(float(tl_ms[i]) / n_tl * 1e3, 1) for i, ph in enumerate(nat.PHASES) if tl_ms[i] > 0}
         res["timeline_end_us"]["step"] = round(float(step_ms_tl.mean()) * 1e3, 1)
+    # LAST use of this state: everything above (per-kernel profile, roofline, timeline) saw the particles of `value`
+    if want_hot if want_t0 is None else want_t0:
+        # the same K device-timed steps (cold L2, events, max over ranks) but from t = 0 on re-initialised particles and
+        # optimizer state: the steps a sample() call really executes
+        key0 = PRNGKey(0)
+        key0, subk0 = split(key0, 2)
+        init0 = model._sample_initial_random_particles(key=subk0, n_particles=m, n_dim=d, plan=plan)
+        z0_all, th0_all = init0 if joint else (init0, None)
+        z.copy_(z0_all[lo:hi]); v_z.zero_(); sf.zero_()
+        if joint:
+            theta.copy_(th0_all[lo:hi]); v_th.zero_()
+        key_dev.copy_(keys_to_device(key0, device))
+        ctx.barrier()
+        ms0, _ = steps_timed(0, K, per_kernel=False)
+        res["value_from_t0"] = K / (ctx.max_over_ranks(float(ms0.sum())) / 1e3)
+        ctx.barrier()
     res.update(kernels=kernels, roofline=roofline, model=model, t_next=t)
     return res
 
@@ -613,9 +635,10 @@ def run_native(args):
     also = {}
     for other in ([] if args.no_also else [w for w in ("c2", "t_bge", "c3") if w != name]):
         o_steps = {"c3": 20}.get(other, 50)
-        r = measure_workload(ctx, other, o_steps, 3, min(o_steps, 10), want_hot=False)
+        r = measure_workload(ctx, other, o_steps, 3, min(o_steps, 10), want_hot=False, want_t0=True)
         rl = r["roofline"] or {}
-        also[other] = {"workload": WORKLOADS[other][0], "value": r["value"], "unit": "steps/s", "ms_per_step": r["ms_per_step"],
+        also[other] = {"workload": WORKLOADS[other][0], "value": r["value"], "value_from_t0": r.get("value_from_t0"), "t_start": T_MID,
+                       "unit": "steps/s", "ms_per_step": r["ms_per_step"],
                        "steps": o_steps, "dominant_kernel": rl.get("kernel"), "frac": rl.get("frac"), "bound": rl.get("bound"),
                        "us_per_launch": rl.get("us_per_launch"),
                        "kernels_us": {k_: v["us"] for k_, v in r["kernels"].items()}}
@@ -647,6 +670,7 @@ def run_native(args):
         "config": cfg,
         "graphs_scored_per_sec": value * m * s * n_passes,
         "value_l2_resident": res.get("value_l2_resident"),
+        "value_from_t0": res.get("value_from_t0"),
         "gpu_launches": res["launches"],
         "clocks": clocks,
         "e2e": {"value": K / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes / K, "d2h_bytes_per_step": d2h_bytes / K,

@@ -13,7 +13,7 @@ import subprocess
 import sys
 
 PHASE_OF = [("k_mc_", None), ("k_acyclic", "acyclic"), ("k_pair_dist", "pair_dist"), ("k_pair_finish", "pair_kernel"), ("k_phi", "phi_update"),
-            ("k_prologue", "scores")]
+            ("k_prologue", "scores"), ("k_edge_probs", "scores")]
 
 
 def main(rep, workload, out):
