@@ -147,7 +147,10 @@ def kernel_work(name, m_loc, m_all):
         w["mc_theta"] = dict(flops=m_loc * (s * fwd_bwd + edge), bytes=m_loc * 4 * (dz + 2 * dth), bound="fp32")
         w["mc_z"] = dict(flops=m_loc * (s * fwd_bwd + edge), bytes=m_loc * 4 * (dz + dth + d * d), bound="fp32")
     else:
-        # one Cholesky of the (l+1)x(l+1) parent block per (graph, node); l ~ d/2 at P = 0.5 -> (d/2)^3/3 flops, fp64
+        # one Cholesky of the (l+1)x(l+1) parent block per (graph, node); l ~ d/2 at P = 0.5 -> (d/2)^3/3 flops, fp64.
+        # NOTE: this charges the work of the HIGH-entropy regime (t = 0).  At `value`'s operating point (t >= 100) the
+        # kernel does far less (common parents eliminated once per particle and node, kernels_mc_bge.cuh:13-22), so the
+        # frac reported for mc_z there is not pipe utilisation; at t = 0 it is 8-17x lower (profiles/r02/RESULTS.md)
         chol = d * ((d / 2.0) ** 3) / 3.0
         w["mc_z"] = dict(flops=m_loc * (s * chol + edge), bytes=m_loc * 4 * (dz + d * d), bound="fp64")
     nmat = (int(np.floor(np.log2(max(d - 1, 1)))) + bin(max(d - 1, 1)).count("1") - 1)

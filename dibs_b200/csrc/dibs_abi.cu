@@ -434,11 +434,10 @@ extern "C" int dibs_plan_create(const dibs_config* cfg, dibs_plan** out) {
         if (ns < 1) ns = 1;
         p->j_len = ceil_div(ceil_div(p->M, ns), PT_J) * PT_J;
         p->n_jsplit = ceil_div(p->M, p->j_len);
-        // tensor-core phi (>= MMA_MIN_PARTICLES particles, see phi_mma_eligible): a CTA pays a fixed pipeline fill /
-        // TMEM / epilogue cost (~5 us, then ~2.8 us per 32 particles: the kernel is bound by the L2 -> SM traffic of
-        // its operand tiles), so slices are longer than the SIMT kernel's -- 256 particles, again a function of M only:
-        // 8 stages per CTA, and still 80 CTAs when 8 ranks own 128 rows each (512-particle slices: 152 us on one GPU
-        // but only 40 CTAs, 78 us, on 8)
+        // tensor-core phi (>= MMA_MIN_PARTICLES particles, see phi_mma_eligible): a CTA pays ~5 us of fixed cost
+        // (pipeline fill, drain, epilogue) and 1.23 us per 32 particles (tools/phi_trace.py: MMA issue 0.77 us of it on a
+        // 2-stage ring), so slices are longer than the SIMT kernel's -- 256 particles, again a function of M only:
+        // 8 stages per CTA, and still 80 CTAs when 8 ranks own 128 rows each
         const int ld_rows = (p->D + 3) & ~3;
         if (phi_mma_eligible(p->M, ld_rows, 512)) {
             p->j_len = 256;
