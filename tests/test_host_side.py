@@ -138,3 +138,14 @@ def test_bench_work_model_covers_every_phase():
             assert np.isfinite(tb) and tb > 0 and "allgather" not in per
         cfg = bench.config_dict(name, 8 if m % 8 == 0 else 1)
         assert cfg["workload"].startswith(name) and cfg["particles_per_gpu"] * (8 if m % 8 == 0 else 1) == m
+
+
+def test_bench_line_reports_steps_from_t0():
+    """`value` is timed from t = T_MID on fresh particles; for BGe that is not what sample() runs (profiles/r02/RESULTS.md),
+    so the line must also carry `value_from_t0` -- for the main workload and for every `also` entry."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "bench.py")).read()
+    assert '"value_from_t0": res.get("value_from_t0")' in src
+    assert '"value_from_t0": r.get("value_from_t0")' in src and "want_t0=True" in src
+    assert "steps_timed(0, K, per_kernel=False)" in src           # from step 0, same timing call as `value`
