@@ -231,8 +231,17 @@ VARIANT_CASES = [("lingauss", 20, 8, 32), ("densenn", 20, 8, 32), ("bge", 20, 8,
                  ("densenn", 32, 4, 8)]
 
 
-@pytest.mark.parametrize("lik,d,m,s", VARIANT_CASES)
-def test_step_vs_oracle_n_vars_20(lik, d, m, s):
+# BGe again at a HIGH-ENTROPY operating point (t = 1: alpha = 1, edge probabilities spread over (0.1, 0.9)).  k_mc_bge
+# eliminates the parents common to all samples of a particle once and lets every sample factorise only its "uncertain"
+# subset (kernels_mc_bge.cuh:13-22); at t = 40 the draws of a particle are nearly identical and only that fast path runs.
+# Near t = 0 -- where every run starts -- the common set is empty and every lane factorises a ~d/2-sized block: the path
+# that dominates the first steps of MarginalDiBS (profiles/r02/RESULTS.md) had no parity case above n_vars = 6.
+# (Not t = 0 itself: alpha = 0 makes the score-function estimator identically zero, the comparison would be vacuous.)
+HIGH_ENTROPY_CASES = [("bge", 20, 8, 32), ("bge", 40, 4, 8), ("bge", 50, 4, 16), ("bge", 64, 3, 8)]
+
+
+@pytest.mark.parametrize("lik,d,m,s,t", [c + (40,) for c in VARIANT_CASES] + [c + (1,) for c in HIGH_ENTROPY_CASES])
+def test_step_vs_oracle_n_vars_20(lik, d, m, s, t):
     """BASELINE-shaped problems (n_vars=20, N=100; larger n_vars for the n_vars > 32 kernels) at a particle count the
     oracle finishes in seconds: values vs the fp32 oracle at 1e-5, estimators bounded by the fp32-vs-fp64 oracle gap."""
     from dibs_b200.inference import PRNGKey
@@ -242,7 +251,6 @@ def test_step_vs_oracle_n_vars_20(lik, d, m, s):
     key = PRNGKey(3)
     st32 = orc.init_particles(cfg, key, m, None, np.float32)
     st32.z = (st32.z * 2.0).astype(np.float32)
-    t = 40
     x, mask = g["x"], np.zeros(g["x"].shape, np.int32)
     keys = tf.split(tf.prng_key(9), m)
     alpha = orc.alpha_of(cfg, t, np.float32)
@@ -253,6 +261,10 @@ def test_step_vs_oracle_n_vars_20(lik, d, m, s):
     p = orc.edge_probs(st32.z, alpha)
     gs = np.stack([orc.sample_g(p[i], keys[i], cfg.n_grad_mc_samples) for i in range(m)])
     assert (npy(model.sample_g(p, keys, cfg.n_grad_mc_samples)) == gs).all()
+    if t < 40:
+        # the case is only worth its name if the samples of a particle really differ: hardly any parent common to all
+        common = gs.min(axis=1).sum() / gs.max(axis=1).sum()
+        assert 0.02 < p[p > 0].mean() < 0.98 and common < 0.2, ("not a high-entropy case", float(p.mean()), float(common))
     pre = orc.bge_precompute(x, mask, cfg.lik, np.float64) if lik == "bge" else None
     lp64 = np.stack([orc.log_joint(cfg, gs[i], None if st32.theta is None else orc.theta_for_model(cfg, st32.theta[i].astype(np.float64)),
                                    x, mask, np.float64, want_grads=False, pre=pre)[0] for i in range(m)])
